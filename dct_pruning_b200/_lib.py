@@ -1,0 +1,79 @@
+"""ctypes binding of libdctp.so - the only route from Python to the scoring kernels.
+
+Mirrors include/dctp.h one to one.  Loading fails loudly: a missing library or a missing
+CUDA device is an error, never a reason to compute on the CPU.
+"""
+import ctypes
+import os
+
+from .build import LIB_PATH
+
+PATH_AUTO, PATH_UMMA, PATH_SIMT = 0, 1, 2
+PATHS = {'auto': PATH_AUTO, 'umma': PATH_UMMA, 'simt': PATH_SIMT}
+
+OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_DEVICE = 0, -1, -2, -3, -4
+
+_c = ctypes
+_SIGNATURES = {
+    'dctp_version': (_c.c_int, []),
+    'dctp_last_error': (_c.c_char_p, []),
+    'dctp_init': (_c.c_int, []),
+    'dctp_shutdown': (_c.c_int, []),
+    'dctp_prepare': (_c.c_int, [_c.c_int, _c.c_int]),
+    'dctp_score_accum': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
+                                    _c.c_longlong, _c.c_longlong, _c.c_longlong,
+                                    _c.c_int, _c.c_int,
+                                    _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                    _c.c_int, _c.c_void_p]),
+    'dctp_finalize': (_c.c_int, [_c.c_void_p, _c.c_double, _c.c_void_p, _c.c_int, _c.c_void_p]),
+    'dctp_topk_segmented': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
+                                       _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'dctp_check': (_c.c_int, [_c.c_void_p]),
+    'dctp_score_host': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                   _c.c_void_p, _c.c_int]),
+    'dctp_path_for': (_c.c_int, [_c.c_int, _c.c_int, _c.c_longlong]),
+    'dctp_launch_count': (_c.c_longlong, []),
+    'dctp_sm_count': (_c.c_int, []),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+
+class DctpError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__('libdctp error %d: %s' % (code, text))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen libdctp.so (built in-tree by dct_pruning_b200.build) and type its entry points."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('libdctp.so not found at %s: run `python -c "import __graft_entry__ as g; g.build()"` '
+                          '(or python -m dct_pruning_b200.build); there is no CPU fallback' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = the .so is stale w.r.t. include/dctp.h
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != OK:
+        raise DctpError(code, load().dctp_last_error().decode('utf-8', 'replace'))
+    return code
+
+
+def ptr(t):
+    """Device/host address of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

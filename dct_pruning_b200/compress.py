@@ -67,10 +67,11 @@ def selection_plan(net_name, rates) -> List[Selection]:
     orig, pruned, ow, pw = _shapes(net_name, rates)
     plan = []
 
-    def consider(conv, stem):
+    def consider(conv, stem, even_if_full=False):
         C, k = ow[conv][0], pw[conv][0]
-        if C != k:
+        if C != k or even_if_full:
             plan.append(Selection(stem, C, k, conv + '.weight'))
+        return C != k
 
     if net_name in ('vgg_16_bn', 'densenet_40'):         # load_models.py:24-41, 394-409
         for cnt, conv in enumerate(ow, start=1):
@@ -104,7 +105,9 @@ def selection_plan(net_name, rates) -> List[Selection]:
                 consider(name + '.branch5x5.3', 'imp_conv%d_n5x5' % cnt)
                 consider(name + '.branch5x5.6', 'imp_conv%d_n5x5' % cnt)
     elif net_name == 'u2netp':                            # load_models.py:595-748
-        side = 0
+        # once one conv has been pruned (`last_select_index is not None`, load_models.py:647,689,725)
+        # the loader argsorts every later stage conv too, even at k == C (it then keeps all channels)
+        side, pruned_before = 0, False
         for conv in ow:
             if conv == 'outconv':
                 break
@@ -113,7 +116,7 @@ def selection_plan(net_name, rates) -> List[Selection]:
                 consider(conv, 'net.side%d' % side)
             else:
                 stage, block = conv.split('.')[:2]
-                consider(conv, 'net.%s.%s.relu_s1' % (stage, block))
+                pruned_before |= consider(conv, 'net.%s.%s.relu_s1' % (stage, block), even_if_full=pruned_before)
     else:
         raise ValueError('the network name you have entered is not supported yet: %r' % (net_name,))
     return plan

@@ -1,0 +1,385 @@
+// libdctp.so - C ABI (include/dctp.h) over the sm_100a DCT importance-score kernels.
+// Host side only: argument checks, cosine-basis cache, kernel selection and launch geometry.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "../../include/dctp.h"
+#include "score_simt.cuh"
+#include "score_umma.cuh"
+#include "topk.cuh"
+
+namespace {
+
+using namespace dctp;
+
+thread_local char g_err[512] = "";
+std::mutex g_mu;
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) return fail(DCTP_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));       \
+    } while (0)
+
+struct UmmaBasis { uint16_t *hi = nullptr, *lo = nullptr; };            // [KP x KP] block-diagonal I_J (x) C_N
+struct SimtBasis { float* t = nullptr; };                               // [N x N], t[n*N + k] = C_N[k][n]
+
+struct State {
+    bool ready = false;
+    int device = -1, sm_count = 0;
+    int* status = nullptr;
+    long long launches = 0;
+    std::map<std::pair<int, int>, UmmaBasis> umma;     // (N, KP)
+    std::map<int, SimtBasis> simt;                     // N
+    int occ[2][3] = {{0, 0, 0}, {0, 0, 0}};            // resident CTAs/SM per (KP, VEC) instantiation
+    // scratch of dctp_score_host (grow-only)
+    float* hx = nullptr; size_t hx_bytes = 0;
+    double* hacc = nullptr; float* hout = nullptr; size_t hc = 0;
+} g;
+
+// ------------------------------------------------------------------ cosine bases
+inline double dct_coef(int k, int n, int N) {          // orthonormal DCT-II: C_N[k][n]
+    const double s = k == 0 ? std::sqrt(1.0 / N) : std::sqrt(2.0 / N);
+    return s * std::cos(M_PI * (2.0 * n + 1.0) * k / (2.0 * N));
+}
+inline uint16_t bf16_rn(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>(u >> 16);
+}
+inline float bf16_to_f(uint16_t b) {
+    uint32_t u = static_cast<uint32_t>(b) << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+inline void split_bf16(double c, uint16_t& hi, uint16_t& lo) {
+    hi = bf16_rn(static_cast<float>(c));
+    lo = bf16_rn(static_cast<float>(c - static_cast<double>(bf16_to_f(hi))));
+}
+
+int get_umma_basis(int N, int KP, UmmaBasis& out) {
+    auto key = std::make_pair(N, KP);
+    auto it = g.umma.find(key);
+    if (it != g.umma.end()) { out = it->second; return DCTP_OK; }
+    const int Ms = (N + 7) / 8 * 8, J = KP / Ms;
+    std::vector<uint16_t> hi(static_cast<size_t>(KP) * KP, 0), lo(hi.size(), 0);
+    for (int j = 0; j < J; ++j)
+        for (int v = 0; v < N; ++v)
+            for (int w = 0; w < N; ++w)
+                split_bf16(dct_coef(v, w, N), hi[(size_t)(j * Ms + v) * KP + j * Ms + w], lo[(size_t)(j * Ms + v) * KP + j * Ms + w]);
+    UmmaBasis b;
+    CUDA_TRY(cudaMalloc(&b.hi, hi.size() * 2));
+    CUDA_TRY(cudaMalloc(&b.lo, lo.size() * 2));
+    CUDA_TRY(cudaMemcpy(b.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    g.umma[key] = b;
+    out = b;
+    return DCTP_OK;
+}
+
+int get_simt_basis(int N, SimtBasis& out) {
+    auto it = g.simt.find(N);
+    if (it != g.simt.end()) { out = it->second; return DCTP_OK; }
+    std::vector<float> t(static_cast<size_t>(N) * N);
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < N; ++k) t[(size_t)n * N + k] = static_cast<float>(dct_coef(k, n, N));
+    SimtBasis b;
+    CUDA_TRY(cudaMalloc(&b.t, t.size() * 4));
+    CUDA_TRY(cudaMemcpy(b.t, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+    g.simt[N] = b;
+    out = b;
+    return DCTP_OK;
+}
+
+// ------------------------------------------------------------------ init
+template <int KP, int VEC>
+int setup_umma(int& occ) {
+    auto* fn = score_umma_kernel<KP, VEC>;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaScoreSmem<KP>::TOTAL));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, UmmaScoreSmem<KP>::TOTAL));
+    if (occ < 1) return fail(DCTP_E_CUDA, "score_umma_kernel<%d,%d> does not fit on an SM", KP, VEC);
+    const int by_tmem = 512 / static_cast<int>(UmmaScoreSmem<KP>::TMEM_COLS);   // TMEM columns are a per-SM resource too
+    if (occ > by_tmem) occ = by_tmem;
+    return DCTP_OK;
+}
+
+int ensure_init() {
+    if (g.ready) return DCTP_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(DCTP_E_UNSUPPORTED, "libdctp is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+    g.device = dev;
+    g.sm_count = prop.multiProcessorCount;
+    int rc;
+    if ((rc = setup_umma<64, 4>(g.occ[0][0]))) return rc;
+    if ((rc = setup_umma<64, 2>(g.occ[0][1]))) return rc;
+    if ((rc = setup_umma<64, 1>(g.occ[0][2]))) return rc;
+    if ((rc = setup_umma<128, 4>(g.occ[1][0]))) return rc;
+    if ((rc = setup_umma<128, 2>(g.occ[1][1]))) return rc;
+    if ((rc = setup_umma<128, 1>(g.occ[1][2]))) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(score_simt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMALL_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(score_simt_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaMalloc(&g.status, sizeof(int)));
+    CUDA_TRY(cudaMemset(g.status, 0, sizeof(int)));
+    g.ready = true;
+    return DCTP_OK;
+}
+
+inline int pow2_floor(int v) {
+    int p = 1;
+    while (p * 2 <= v) p *= 2;
+    return p;
+}
+
+bool umma_shape_ok(int H, int W, long long stride_h) { return H == W && H >= 1 && H <= 128 && stride_h == W; }
+
+int pick_vec(const float* x, long long stride_b, long long stride_c, int c_begin, int N) {
+    auto aligned = [&](int v) {
+        return (N % v) == 0 && (reinterpret_cast<uintptr_t>(x) % (4 * v)) == 0 && (stride_b % v) == 0 && (stride_c % v) == 0;
+    };
+    (void)c_begin;
+    if (aligned(4)) return 4;
+    if (aligned(2)) return 2;
+    return 1;
+}
+
+template <int KP>
+int launch_umma(const float* x, int B, int N, long long stride_b, long long stride_c, int c_begin, int c_count,
+                double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
+    UmmaBasis basis;
+    int rc = get_umma_basis(N, KP, basis);
+    if (rc) return rc;
+    UmmaScoreArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.c_begin = c_begin; a.c_count = c_count;
+    a.n_maps = B * c_count;
+    a.N = N; a.NN = N * N;
+    a.Ms = (N + 7) / 8 * 8; a.G = 128 / a.Ms; a.J = KP / a.Ms; a.MT = a.G * a.J;
+    a.num_tiles = (a.n_maps + a.MT - 1) / a.MT;
+    a.K1 = (a.J * a.Ms + 15) / 16; a.N1 = 16 * a.K1;
+    if (a.Ms == 8) { a.NQ = a.J / 2; a.K2S = 1; a.N2 = 16; }
+    else { a.NQ = a.J; a.K2S = (a.Ms + 15) / 16; a.N2 = 16 * a.K2S; }
+    a.a2_lbo = static_cast<uint32_t>(a.K2S) * 2048u; a.a2_group_bytes = 2u * a.a2_lbo;
+    a.TPM = pow2_floor(128 / a.MT < 32 ? 128 / a.MT : 32);
+    a.idesc1 = umma::make_idesc_bf16(128, a.N1, false, false);
+    a.idesc2 = umma::make_idesc_bf16(128, a.N2, true, false);
+    const int vec = pick_vec(x, stride_b, stride_c, c_begin, N);
+    a.div_vpm.set(a.NN / vec); a.div_n.set(N); a.div_ms.set(a.Ms); a.div_j.set(a.J);
+    a.basis_hi = basis.hi; a.basis_lo = basis.lo;
+    a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
+    const int kpi = KP == 64 ? 0 : 1, vi = vec == 4 ? 0 : vec == 2 ? 1 : 2;
+    int grid = g.sm_count * g.occ[kpi][vi];
+    if (grid > a.num_tiles) grid = a.num_tiles;
+    const size_t smem = UmmaScoreSmem<KP>::TOTAL;
+    if (vec == 4) score_umma_kernel<KP, 4><<<grid, 128, smem, stream>>>(a);
+    else if (vec == 2) score_umma_kernel<KP, 2><<<grid, 128, smem, stream>>>(a);
+    else score_umma_kernel<KP, 1><<<grid, 128, smem, stream>>>(a);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    return DCTP_OK;
+}
+
+int launch_simt(const float* x, int B, int H, int W, long long stride_b, long long stride_c, long long stride_h,
+                int c_begin, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
+    SimtBasis bh, bw;
+    int rc = get_simt_basis(H, bh);
+    if (rc) return rc;
+    if ((rc = get_simt_basis(W, bw))) return rc;
+    SimtScoreArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.stride_h = stride_h;
+    a.c_begin = c_begin; a.c_count = c_count; a.n_maps = B * c_count; a.H = H; a.W = W;
+    a.basis_h_t = bh.t; a.basis_w_t = bw.t; a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out;
+    if (H <= SIMT_T && W <= SIMT_T) {
+        const int G = SIMT_T / H, tiles = (a.n_maps + G - 1) / G;
+        int grid = g.sm_count * 2;
+        if (grid > tiles) grid = tiles;
+        score_simt_small_kernel<<<grid, 256, SIMT_SMALL_SMEM, stream>>>(a);
+    } else {
+        const int Hpad = (H + SIMT_T - 1) / SIMT_T * SIMT_T;
+        const size_t smem = static_cast<size_t>(Hpad + 2 * SIMT_T) * SIMT_LD * sizeof(float);
+        if (smem > 200 * 1024) return fail(DCTP_E_UNSUPPORTED, "map height %d needs %zu B of shared memory", H, smem);
+        if (energy_out) CUDA_TRY(cudaMemsetAsync(energy_out, 0, sizeof(float) * a.n_maps, stream));
+        const unsigned grid = static_cast<unsigned>((W + SIMT_T - 1) / SIMT_T) * static_cast<unsigned>(a.n_maps);
+        score_simt_large_kernel<<<grid, 256, smem, stream>>>(a);
+    }
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    return DCTP_OK;
+}
+
+int resolve_path(int path, int H, int W, long long stride_h) {
+    if (path == DCTP_PATH_AUTO) {
+        if (umma_shape_ok(H, W, stride_h)) return DCTP_PATH_UMMA;
+        return DCTP_PATH_SIMT;
+    }
+    return path;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int dctp_version(void) { return DCTP_VERSION; }
+const char* dctp_last_error(void) { return g_err; }
+
+int dctp_init(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return ensure_init();
+}
+
+int dctp_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.ready) return DCTP_OK;
+    for (auto& kv : g.umma) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
+    for (auto& kv : g.simt) cudaFree(kv.second.t);
+    g.umma.clear(); g.simt.clear();
+    cudaFree(g.status); cudaFree(g.hx); cudaFree(g.hacc); cudaFree(g.hout);
+    g = State();
+    return DCTP_OK;
+}
+
+int dctp_sm_count(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_init();
+    return rc ? rc : g.sm_count;
+}
+long long dctp_launch_count(void) { return g.launches; }
+
+int dctp_path_for(int H, int W, long long stride_h) { return resolve_path(DCTP_PATH_AUTO, H, W, stride_h); }
+
+int dctp_prepare(int H, int W) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (H < 1 || W < 1) return fail(DCTP_E_INVALID, "dctp_prepare: H=%d W=%d", H, W);
+    if (umma_shape_ok(H, W, W)) {
+        UmmaBasis b;
+        return get_umma_basis(H, H <= 64 ? 64 : 128, b);
+    }
+    SimtBasis b;
+    if ((rc = get_simt_basis(H, b))) return rc;
+    return get_simt_basis(W, b);
+}
+
+int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, long long stride_c, long long stride_h,
+                     int c_begin, int c_count, double* accum, float* energy_out, float* coeff_out, int path,
+                     void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!x || !accum) return fail(DCTP_E_INVALID, "dctp_score_accum: null pointer");
+    if (B < 0 || H < 1 || W < 1 || c_begin < 0 || c_count < 0 || stride_h < W)
+        return fail(DCTP_E_INVALID, "dctp_score_accum: B=%d H=%d W=%d c_begin=%d c_count=%d stride_h=%lld", B, H, W, c_begin,
+                    c_count, stride_h);
+    if (B == 0 || c_count == 0) return DCTP_OK;                     // empty batch / empty window: nothing to add
+    if (static_cast<long long>(B) * c_count > (1ll << 30)) return fail(DCTP_E_INVALID, "too many maps in one call");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int p = resolve_path(path, H, W, stride_h);
+    switch (p) {
+        case DCTP_PATH_UMMA:
+            if (!umma_shape_ok(H, W, stride_h))
+                return fail(DCTP_E_UNSUPPORTED, "UMMA path takes contiguous square maps of side <= 128 (got %dx%d, stride_h %lld)", H, W,
+                            stride_h);
+            return H <= 64 ? launch_umma<64>(x, B, H, stride_b, stride_c, c_begin, c_count, accum, energy_out, coeff_out, s)
+                           : launch_umma<128>(x, B, H, stride_b, stride_c, c_begin, c_count, accum, energy_out, coeff_out, s);
+        case DCTP_PATH_SIMT:
+            return launch_simt(x, B, H, W, stride_b, stride_c, stride_h, c_begin, c_count, accum, energy_out, coeff_out, s);
+        default:
+            return fail(DCTP_E_INVALID, "unknown path %d", path);
+    }
+}
+
+int dctp_finalize(const double* accum, double n_images, float* out, int n, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!accum || !out)) || !(n_images > 0)) return fail(DCTP_E_INVALID, "dctp_finalize: n=%d n_images=%g", n, n_images);
+    if (n == 0) return DCTP_OK;
+    finalize_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(accum, n_images, out, n);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    return DCTP_OK;
+}
+
+int dctp_topk_segmented(const float* scores, const int* seg_offsets, const int* seg_k, int n_seg, long long* out_idx,
+                        const int* out_offsets, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (n_seg < 0 || (n_seg > 0 && (!scores || !seg_offsets || !seg_k || !out_idx || !out_offsets)))
+        return fail(DCTP_E_INVALID, "dctp_topk_segmented: null pointer or n_seg=%d", n_seg);
+    if (n_seg == 0) return DCTP_OK;
+    topk_segmented_kernel<<<n_seg, TOPK_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(scores, seg_offsets, seg_k, out_idx,
+                                                                                         out_offsets);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    return DCTP_OK;
+}
+
+int dctp_check(void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_init();
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    int st = 0;
+    CUDA_TRY(cudaMemcpy(&st, g.status, sizeof st, cudaMemcpyDeviceToHost));
+    if (st != 0) {
+        cudaMemset(g.status, 0, sizeof(int));
+        return fail(DCTP_E_DEVICE, "device status %d: a tensor-core completion wait timed out", st);
+    }
+    return DCTP_OK;
+}
+
+int dctp_score_host(const float* x_host, int B, int C, int H, int W, int c_begin, int c_count, float* scores_host, int path) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int rc = ensure_init();
+        if (rc) return rc;
+        if (!x_host || !scores_host || B < 1 || C < 1 || H < 1 || W < 1 || c_begin < 0 || c_count < 1 || c_begin + c_count > C)
+            return fail(DCTP_E_INVALID, "dctp_score_host: B=%d C=%d H=%d W=%d window [%d,+%d)", B, C, H, W, c_begin, c_count);
+        const size_t bytes = sizeof(float) * B * C * H * W;
+        if (bytes > g.hx_bytes) {
+            cudaFree(g.hx);
+            g.hx = nullptr; g.hx_bytes = 0;
+            CUDA_TRY(cudaMalloc(&g.hx, bytes));
+            g.hx_bytes = bytes;
+        }
+        if (static_cast<size_t>(c_count) > g.hc) {
+            cudaFree(g.hacc); cudaFree(g.hout);
+            g.hacc = nullptr; g.hout = nullptr; g.hc = 0;
+            CUDA_TRY(cudaMalloc(&g.hacc, sizeof(double) * c_count));
+            CUDA_TRY(cudaMalloc(&g.hout, sizeof(float) * c_count));
+            g.hc = c_count;
+        }
+        CUDA_TRY(cudaMemcpyAsync(g.hx, x_host, bytes, cudaMemcpyHostToDevice, 0));
+        CUDA_TRY(cudaMemsetAsync(g.hacc, 0, sizeof(double) * c_count, 0));
+    }
+    int rc = dctp_score_accum(g.hx, B, H, W, static_cast<long long>(C) * H * W, static_cast<long long>(H) * W, W, c_begin, c_count,
+                              g.hacc, nullptr, nullptr, path, nullptr);
+    if (rc) return rc;
+    if ((rc = dctp_finalize(g.hacc, static_cast<double>(B), g.hout, c_count, nullptr))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(scores_host, g.hout, sizeof(float) * c_count, cudaMemcpyDeviceToHost, 0));
+    return dctp_check(nullptr);
+}
+
+}  // extern "C"

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) score_simt_small_kernel(const SimtScoreAr
     }
 }
 
-// grid = (panels, n_maps); dynamic smem = Ybuf[Hpad][SIMT_LD] + 2 staging tiles
+// grid = n_maps * panels (map-major); dynamic smem = Ybuf[Hpad][SIMT_LD] + 2 staging tiles
 __global__ void __launch_bounds__(256) score_simt_large_kernel(const SimtScoreArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int H = a.H, W = a.W;
@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(256) score_simt_large_kernel(const SimtScoreAr
     float (*Ts)[SIMT_LD] = reinterpret_cast<float (*)[SIMT_LD]>(smem_f + Hpad * SIMT_LD);        // X block / C_H block
     float (*Bs)[SIMT_LD] = reinterpret_cast<float (*)[SIMT_LD]>(smem_f + (Hpad + SIMT_T) * SIMT_LD);
     __shared__ float scratch[8];
-    const int tid = threadIdx.x, m = blockIdx.y, v0 = blockIdx.x * SIMT_T;
+    const int panels = (W + SIMT_T - 1) / SIMT_T;
+    const int tid = threadIdx.x, m = blockIdx.x / panels, v0 = (blockIdx.x % panels) * SIMT_T;
     const float* xm = simt_map_ptr(a, m);
     const int row = tid >> 2, cq = (tid & 3) * 16;      // thread owns 1 row x 16 columns of a 64x64 block
 

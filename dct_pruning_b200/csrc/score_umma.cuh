@@ -3,20 +3,27 @@
 // Replaces, for one hooked activation, the per-slice Python loop of
 // /root/reference/utils/common.py:262-277 (dct_2d per (image, channel) -> sum of squared
 // coefficients -> per-channel batch sum).  One launch reads every scored map from HBM exactly
-// once, keeps the cosine basis resident in shared memory, runs C_H * X * C_W^T on tensor cores
+// once, keeps the cosine basis resident in shared memory, runs C_N * X * C_N^T on tensor cores
 // and reduces the coefficients to energies straight out of TMEM: no coefficient tensor is ever
 // written to HBM (unless the debug `dump` pointer asks for it).
 //
-// Tile = 128 TMEM lanes.
-//   TWO_STAGE (9 <= N <= 128):  G = 128 / Ms maps per tile (Ms = N rounded up to 8), lane = g*Ms + h.
-//     stage 1  D1[(g,h), v] = sum_w  X_g[h,w]   * C[v,w]      A1 = split(X) K-major   (K = w)
-//     epi   1  D1 -> bf16 hi/lo -> A2[(g,v), h]                A2 MN-major            (K = h)
-//     stage 2  D2[(g,v), u] = sum_h  A2[(g,v),h] * C[u,h]  ==  Z_g[u,v]
-//     epi   2  energy_g = sum_{u,v} D2^2  (fixed-order fp32 tree) -> fp64 atomicAdd per channel
-//   single stage (N <= 8): lane = map, K = flattened map (N*N <= 64), basis = C (x) C (Kronecker),
-//     D1[g, (u,v)] = Z_g[u,v], energy straight from the lane's row.
+// Tile = 128 TMEM lanes x KP contraction columns, packed with G x J square maps of side N:
+//   Ms = N rounded up to 8            lanes (and contraction columns) one map occupies
+//   G  = 128 / Ms  lane groups,  J = KP / Ms  column groups,  map t of the tile sits at (g, j) = (t / J, t % J)
+//
+//   stage 1   D1[(g,h), (j,v)] = sum_{(j',w)} A1[(g,h), (j',w)] * B[(j,v), (j',w)]
+//             A1[(g,h),(j,w)] = X_{g,j}[h,w]   K-major;  B = I_J (x) C_N  (block diagonal, zero padded)
+//             -> D1[(g,h),(j,v)] = Y_{g,j}[h,v] = (X C^T)[h,v]
+//   epi   1   D1 -> bf16 hi/lo -> A2_q[(g,v), k]   MN-major (transpose-free: a lane writes along M)
+//   stage 2   per column group q:  D2[(g,v), q*N2 + u] = sum_h A2_q[(g,v), h] * C[u, h] = Z_{g,j}[u,v]
+//             (the top-left corner of B is C itself, so stage 2 re-uses the resident basis;
+//              for Ms == 8 two column groups share one K=16 step: q = j/2, k = (j%2)*8 + h)
+//   epi   2   energy_{g,j} = sum_{u,v} D2^2  (fixed-order fp32 tree) -> one fp64 atomicAdd per map
+//
 // Every product runs as three bf16 MMAs: hi*hi + lo*hi + hi*lo (fp32 accumulate in TMEM).
 // Operands live in shared memory in the canonical SWIZZLE_128B layouts (8-row x 128-byte atoms).
+// A2 re-uses A1's storage (stage 1 has completed when epilogue 1 runs).  Positions of A1/A2 that
+// a tile does not write hold finite bf16 leftovers; they only ever meet zero entries of B.
 #pragma once
 #include "umma.cuh"
 
@@ -28,23 +35,29 @@ struct FastDiv {            // q = n / d for n < 2^32 / d
     __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : __umulhi(n, mul); }
 };
 
+enum : int { DCTP_DEV_OK = 0, DCTP_DEV_MMA_TIMEOUT = 1 };
+
 struct UmmaScoreArgs {
-    const float* x;                 // activation base pointer (fp32, maps contiguous: stride_h = W, stride_w = 1)
+    const float* x;                 // activation base pointer (fp32, maps contiguous: stride_h = N, stride_w = 1)
     long long stride_b, stride_c;   // in elements
     int c_begin, c_count;           // scored channel window (DenseNet: last 12)
     int n_maps;                     // B * c_count
-    int N;                          // map side (H == W)
-    int NN;                         // N * N
-    int row_len;                    // TWO_STAGE: N ; single stage: N*N
-    int Ms;                         // TMEM lanes per map (TWO_STAGE: roundup8(N); single: 1)
-    int G;                          // maps per tile = 128 / Ms
+    int N, NN;                      // map side (H == W), N*N
+    int Ms, G, J, MT;               // lanes per map, lane groups, column groups, maps per tile (G*J)
     int num_tiles;
-    FastDiv div_vpm, div_row, div_ms;
-    const uint16_t* basis_hi;       // [KP x KP] bf16 bits, row = output index, col = contraction index, zero padded
+    int K1;                         // stage-1 k-steps (16 columns each) = ceil(J*Ms / 16)
+    int N1;                         // stage-1 output columns = 16*K1
+    int NQ, K2S, N2;                // stage-2: groups, k-steps per group, output columns per group
+    int TPM;                        // threads per map in the final reduction (power of two <= 32, TPM*MT <= 128)
+    uint32_t idesc1, idesc2;
+    uint32_t a2_lbo, a2_group_bytes;
+    FastDiv div_vpm, div_n, div_ms, div_j;
+    const uint16_t* basis_hi;       // [KP x KP] bf16 bits of I_J (x) C_N, row = output index, col = contraction index
     const uint16_t* basis_lo;
     double* accum;                  // [c_count] per-channel energy sums (fp64)
     float* energy_out;              // optional [n_maps] per-(image,channel) energies
-    float* dump;                    // optional [n_maps x NN] DCT coefficients (debug / parity of the transform itself)
+    float* dump;                    // optional [n_maps x NN] DCT coefficients Z[u][v] (parity of the transform itself)
+    int* status;                    // device status word (DCTP_DEV_*)
 };
 
 namespace detail {
@@ -96,50 +109,43 @@ template <> struct Ld<1> {
     }
 };
 
-constexpr uint32_t tmem_cols_for(int need) {
-    return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
-}
-
 }  // namespace detail
 
-template <int KP, bool TWO_STAGE>
+template <int KP>
 struct UmmaScoreSmem {
-    static constexpr uint32_t KB = (KP + 63) / 64;                 // 64-element K blocks
-    static constexpr uint32_t A_BYTES = KB * 128u * 128u;          // one 128-row K-major operand (hi or lo)
-    static constexpr uint32_t A2_BYTES = 128u * KP * 2u;           // MN-major operand: 2 M blocks x KP/8 atoms
+    static_assert(KP == 64 || KP == 128, "contraction width");
+    static constexpr uint32_t KB = KP / 64;                        // 64-element K blocks
+    static constexpr uint32_t A_BYTES = KB * 128u * 128u;          // one 128-row operand (hi or lo); A2 aliases it
     static constexpr uint32_t B_BYTES = KB * KP * 128u;
-    static constexpr uint32_t OFF_A1_HI = 0;
-    static constexpr uint32_t OFF_A1_LO = OFF_A1_HI + A_BYTES;
-    static constexpr uint32_t OFF_A2_HI = OFF_A1_LO + A_BYTES;
-    static constexpr uint32_t OFF_A2_LO = OFF_A2_HI + (TWO_STAGE ? A2_BYTES : 0);
-    static constexpr uint32_t OFF_B_HI = OFF_A2_LO + (TWO_STAGE ? A2_BYTES : 0);
+    static constexpr uint32_t OFF_A_HI = 0;
+    static constexpr uint32_t OFF_A_LO = OFF_A_HI + A_BYTES;
+    static constexpr uint32_t OFF_B_HI = OFF_A_LO + A_BYTES;
     static constexpr uint32_t OFF_B_LO = OFF_B_HI + B_BYTES;
-    static constexpr uint32_t OFF_MISC = OFF_B_LO + B_BYTES;       // barrier, tmem slot, reduction scratch
-    static constexpr uint32_t MISC_BYTES = 16 + 128 * 4 + 128 * 8;
+    static constexpr uint32_t OFF_MISC = OFF_B_LO + B_BYTES;       // barrier, tmem slot, map pointers, reduction scratch
+    static constexpr uint32_t RED_FLOATS = 8 * 128;                // [J <= 8][128 lanes]
+    static constexpr uint32_t MISC_BYTES = 16 + 128 * 8 + RED_FLOATS * 4;
     static constexpr uint32_t TOTAL = OFF_MISC + MISC_BYTES + 1024;  // + slack for manual 1024-B alignment
-    static constexpr uint32_t TMEM_COLS = detail::tmem_cols_for(TWO_STAGE ? 2 * KP : KP);
+    static constexpr uint32_t TMEM_COLS = 2 * KP;                  // D1 | D2
 };
 
-template <int KP, bool TWO_STAGE, int VEC>
+template <int KP, int VEC>
 __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) {
-    using S = UmmaScoreSmem<KP, TWO_STAGE>;
+    using S = UmmaScoreSmem<KP>;
     using namespace umma;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* a1_hi = smem + S::OFF_A1_HI;
-    uint8_t* a1_lo = smem + S::OFF_A1_LO;
-    uint8_t* a2_hi = smem + S::OFF_A2_HI;
-    uint8_t* a2_lo = smem + S::OFF_A2_LO;
+    uint8_t* a_hi = smem + S::OFF_A_HI;
+    uint8_t* a_lo = smem + S::OFF_A_LO;
     uint8_t* b_hi = smem + S::OFF_B_HI;
     uint8_t* b_lo = smem + S::OFF_B_LO;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::OFF_MISC);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_MISC + 8);
-    float* red = reinterpret_cast<float*>(smem + S::OFF_MISC + 16);
-    const float** mptr = reinterpret_cast<const float**>(smem + S::OFF_MISC + 16 + 128 * 4);   // per-tile map base pointers
+    const float** mptr = reinterpret_cast<const float**>(smem + S::OFF_MISC + 16);   // per-tile map base pointers
+    float* red = reinterpret_cast<float*>(smem + S::OFF_MISC + 16 + 128 * 8);
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
 
-    // ---- one-time setup: zero operands (pad rows/cols must stay finite zeros), stage the basis, TMEM, barrier
+    // ---- one-time setup: zero the operand area, stage the basis, TMEM, barrier
     for (uint32_t off = tid * 16; off < S::OFF_B_HI; off += 128 * 16)
         *reinterpret_cast<uint4*>(smem + off) = make_uint4(0, 0, 0, 0);
     for (uint32_t i = tid; i < KP * (KP / 8); i += 128) {
@@ -162,25 +168,27 @@ __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) 
     const uint32_t tmem = *tmem_slot;
     const uint32_t tmem_lane = tmem + ((warp * 32u) << 16);
 
-    constexpr uint32_t IDESC1 = make_idesc_bf16(128, KP, false, false);
-    constexpr uint32_t IDESC2 = make_idesc_bf16(128, KP, true, false);
-    constexpr uint32_t A2_LBO = (KP / 8) * 1024u;
-    const uint64_t d_a1_hi = make_smem_desc(smem_u32(a1_hi), 16, 1024, SWIZZLE_128B);
-    const uint64_t d_a1_lo = make_smem_desc(smem_u32(a1_lo), 16, 1024, SWIZZLE_128B);
+    const uint64_t d_a_hi = make_smem_desc(smem_u32(a_hi), 16, 1024, SWIZZLE_128B);
+    const uint64_t d_a_lo = make_smem_desc(smem_u32(a_lo), 16, 1024, SWIZZLE_128B);
     const uint64_t d_b_hi = make_smem_desc(smem_u32(b_hi), 16, 1024, SWIZZLE_128B);
     const uint64_t d_b_lo = make_smem_desc(smem_u32(b_lo), 16, 1024, SWIZZLE_128B);
-    const uint64_t d_a2_hi = make_smem_desc(smem_u32(a2_hi), A2_LBO, 1024, SWIZZLE_128B);
-    const uint64_t d_a2_lo = make_smem_desc(smem_u32(a2_lo), A2_LBO, 1024, SWIZZLE_128B);
+    const uint64_t d_a2_hi = make_smem_desc(smem_u32(a_hi), a.a2_lbo, 1024, SWIZZLE_128B);
+    const uint64_t d_a2_lo = make_smem_desc(smem_u32(a_lo), a.a2_lbo, 1024, SWIZZLE_128B);
 
-    // this thread's TMEM lane as (map-in-tile, row-in-map)
+    // this thread's TMEM lane as (lane group, row in map)
     const uint32_t my_g = a.div_ms.div(tid);
     const uint32_t my_r = tid - my_g * a.Ms;
+    const bool lane_in_map = my_g < (uint32_t)a.G && my_r < (uint32_t)a.N;
     const uint32_t vpm = a.NN / VEC;                 // vectors per map
+    const uint32_t used_cols = a.J * a.Ms;
+    const bool ms8 = a.Ms == 8;
+    const uint32_t col_lim = ms8 ? 16u : (uint32_t)a.Ms;   // meaningful D2 columns per stage-2 group
     uint32_t phase = 0;
+    bool alive = true;
 
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        const int map0 = tile * a.G;
-        const int maps_here = min(a.G, a.n_maps - map0);
+    for (int tile = blockIdx.x; tile < a.num_tiles && alive; tile += gridDim.x) {
+        const int map0 = tile * a.MT;
+        const int maps_here = min(a.MT, a.n_maps - map0);
 
         // ---- stage 0: HBM -> registers -> bf16 hi/lo -> A1 (each scored map is read exactly once)
         if ((int)tid < maps_here) {
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) 
         __syncthreads();
         {
             const uint32_t total = maps_here * vpm;
-            constexpr int U = 4;
+            constexpr int U = VEC == 4 ? 8 : 4;
             for (uint32_t base = 0; base < total; base += 128 * U) {
                 float v[U][VEC];
                 uint32_t off[U];
@@ -201,17 +209,17 @@ __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) 
                     uint32_t idx = base + u * 128 + tid;
                     ok[u] = idx < total;
                     if (ok[u]) {
-                        uint32_t g = a.div_vpm.div(idx);
-                        uint32_t e = (idx - g * vpm) * VEC;
-                        uint32_t h = a.div_row.div(e);
-                        uint32_t w = e - h * a.row_len;
-                        detail::Ld<VEC>::ld(mptr[g] + e, v[u]);
-                        off[u] = detail::kmajor_off(g * a.Ms + h, w, 128);
+                        uint32_t t = a.div_vpm.div(idx);
+                        uint32_t e = (idx - t * vpm) * VEC;
+                        uint32_t g = a.div_j.div(t), j = t - g * a.J;
+                        uint32_t h = a.div_n.div(e), w = e - h * a.N;
+                        detail::Ld<VEC>::ld(mptr[t] + e, v[u]);
+                        off[u] = detail::kmajor_off(g * a.Ms + h, j * a.Ms + w, 128);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    if (ok[u]) detail::Ld<VEC>::st(a1_hi, a1_lo, off[u], v[u]);
+                    if (ok[u]) detail::Ld<VEC>::st(a_hi, a_lo, off[u], v[u]);
             }
         }
         fence_async_smem();
@@ -221,130 +229,137 @@ __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) 
         if (tid == 0) {
             tc_fence_after_sync();
             uint32_t acc = 0;
-#pragma unroll
+#pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
-                const uint64_t da = pass == 1 ? d_a1_lo : d_a1_hi;
+                const uint64_t da = pass == 1 ? d_a_lo : d_a_hi;
                 const uint64_t db = pass == 2 ? d_b_lo : d_b_hi;
-#pragma unroll
-                for (uint32_t ks = 0; ks < KP / 16; ++ks) {
+#pragma unroll 1
+                for (uint32_t ks = 0; ks < (uint32_t)a.K1; ++ks) {
                     uint32_t a_off = (ks >> 2) * (128u * 128u) + (ks & 3) * 32u;
                     uint32_t b_off = (ks >> 2) * (KP * 128u) + (ks & 3) * 32u;
-                    mma_bf16_ss(tmem, desc_advance(da, a_off), desc_advance(db, b_off), IDESC1, acc);
+                    mma_bf16_ss(tmem, desc_advance(da, a_off), desc_advance(db, b_off), a.idesc1, acc);
                     acc = 1;
                 }
             }
             mma_commit(bar);
         }
-        mbar_wait(bar, phase);
+        if (!mbar_wait(bar, phase)) alive = false;
         phase ^= 1;
         tc_fence_after_sync();
 
-        const bool lane_valid = (int)my_g < maps_here && my_r < (uint32_t)(TWO_STAGE ? a.N : 1);
-        float energy = 0.f;
-
-        if constexpr (TWO_STAGE) {
-            // ---- epilogue 1: D1 row (g,h) -> bf16 hi/lo -> A2[(g, v), h]   (transpose-free: MN-major operand)
+        // ---- epilogue 1: D1 row (g,h) -> bf16 hi/lo -> A2_q[(g, v), k]   (MN-major operand, aliases A1)
 #pragma unroll 1
-            for (uint32_t c0 = 0; c0 < KP; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tmem_lane + c0, r);
-                tmem_ld_wait();
-                if (lane_valid) {
+        for (uint32_t c0 = 0; c0 < (uint32_t)a.N1; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_lane + c0, r);
+            tmem_ld_wait();
+            if (lane_in_map) {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        uint32_t v0 = c0 + 8 * j;
-                        if (v0 < (uint32_t)a.Ms) {
-                            uint32_t h4[4], l4[4];
+                for (int i = 0; i < 2; ++i) {
+                    uint32_t c = c0 + 8 * i;
+                    if (c < used_cols) {
+                        uint32_t j = a.div_ms.div(c), v0 = c - j * a.Ms;
+                        uint32_t q = ms8 ? (j >> 1) : j;
+                        uint32_t k = ms8 ? ((j & 1) * 8 + my_r) : my_r;
+                        uint32_t h4[4], l4[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                split2(__uint_as_float(r[8 * j + 2 * q]), __uint_as_float(r[8 * j + 2 * q + 1]), h4[q], l4[q]);
-                            uint32_t off = detail::mnmajor_off(my_g * a.Ms + v0, my_r, A2_LBO);
-                            *reinterpret_cast<uint4*>(a2_hi + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-                            *reinterpret_cast<uint4*>(a2_lo + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
-                        }
+                        for (int p = 0; p < 4; ++p)
+                            split2(__uint_as_float(r[8 * i + 2 * p]), __uint_as_float(r[8 * i + 2 * p + 1]), h4[p], l4[p]);
+                        uint32_t off = q * a.a2_group_bytes + detail::mnmajor_off(my_g * a.Ms + v0, k, a.a2_lbo);
+                        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
                     }
                 }
             }
-            tc_fence_before_sync();
-            fence_async_smem();
-            __syncthreads();
+        }
+        tc_fence_before_sync();
+        fence_async_smem();
+        __syncthreads();
 
-            // ---- stage 2 MMA: D2 = A2 * B^T, contraction over the map's rows
-            if (tid == 0) {
-                tc_fence_after_sync();
+        // ---- stage 2 MMA: per column group, D2 = A2_q * C^T, contraction over the map's rows
+        if (tid == 0) {
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (uint32_t q = 0; q < (uint32_t)a.NQ; ++q) {
                 uint32_t acc = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint64_t da = pass == 1 ? d_a2_lo : d_a2_hi;
+                    const uint64_t da = desc_advance(pass == 1 ? d_a2_lo : d_a2_hi, q * a.a2_group_bytes);
                     const uint64_t db = pass == 2 ? d_b_lo : d_b_hi;
-#pragma unroll
-                    for (uint32_t ks = 0; ks < KP / 16; ++ks) {
+#pragma unroll 1
+                    for (uint32_t ks = 0; ks < (uint32_t)a.K2S; ++ks) {
                         uint32_t b_off = (ks >> 2) * (KP * 128u) + (ks & 3) * 32u;
-                        mma_bf16_ss(tmem + KP, desc_advance(da, ks * 2048u), desc_advance(db, b_off), IDESC2, acc);
+                        mma_bf16_ss(tmem + KP + q * a.N2, desc_advance(da, ks * 2048u), desc_advance(db, b_off), a.idesc2,
+                                    acc);
                         acc = 1;
                     }
                 }
-                mma_commit(bar);
             }
-            mbar_wait(bar, phase);
-            phase ^= 1;
-            tc_fence_after_sync();
+            mma_commit(bar);
         }
+        if (!mbar_wait(bar, phase)) alive = false;
+        phase ^= 1;
+        tc_fence_after_sync();
 
-        // ---- final epilogue: coefficients -> energy, never leaving the SM
-        {
-            const uint32_t dcol = TWO_STAGE ? KP : 0;
-            const int m = map0 + (int)my_g;
+        // ---- epilogue 2: coefficients -> energy, never leaving the SM.  Lane = (g, v); column = (q, n).
 #pragma unroll 1
-            for (uint32_t c0 = 0; c0 < KP; c0 += 16) {
+        for (uint32_t q = 0; q < (uint32_t)a.NQ; ++q) {
+            float e0 = 0.f, e1 = 0.f;
+#pragma unroll 1
+            for (uint32_t c0 = 0; c0 < (uint32_t)a.N2; c0 += 16) {
                 uint32_t r[16];
-                tmem_ld16(tmem_lane + dcol + c0, r);
+                tmem_ld16(tmem_lane + KP + q * a.N2 + c0, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float z = __uint_as_float(r[i]);
-                    energy = fmaf(z, z, energy);
+                for (int i = 0; i < 8; ++i) {     // columns past the group's own map(s) hold leftovers: masked
+                    float z0 = c0 + i < col_lim ? __uint_as_float(r[i]) : 0.f;
+                    float z1 = c0 + 8 + i < col_lim ? __uint_as_float(r[8 + i]) : 0.f;
+                    e0 = fmaf(z0, z0, e0);
+                    e1 = fmaf(z1, z1, e1);
                 }
-                if (a.dump != nullptr && lane_valid) {
+                if (a.dump != nullptr && lane_in_map) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        uint32_t col = c0 + i;
-                        if (TWO_STAGE) {       // lane = (g, v), column = u  ->  Z[u][v]
-                            if (col < (uint32_t)a.N) a.dump[(long long)m * a.NN + col * a.N + my_r] = __uint_as_float(r[i]);
-                        } else {               // lane = map, column = u*N + v
-                            if (col < (uint32_t)a.NN) a.dump[(long long)m * a.NN + col] = __uint_as_float(r[i]);
-                        }
+                        uint32_t n = c0 + i;
+                        uint32_t j = ms8 ? (2 * q + (n >> 3)) : q;
+                        uint32_t u = ms8 ? (n & 7) : n;
+                        int t = (int)(my_g * a.J + j);
+                        if (u < (uint32_t)a.N && j < (uint32_t)a.J && t < maps_here)
+                            a.dump[(long long)(map0 + t) * a.NN + u * a.N + my_r] = __uint_as_float(r[i]);
                     }
                 }
             }
-            tc_fence_before_sync();
-            if constexpr (TWO_STAGE) {
-                red[tid] = lane_valid ? energy : 0.f;
-                __syncthreads();
-                for (int g = warp; g < maps_here; g += 4) {
-                    float s = 0.f;
-                    for (int i = lane; i < a.N; i += 32) s += red[g * a.Ms + i];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0) {
-                        int mm = map0 + g;
-                        int c = mm % a.c_count;
-                        atomicAdd(a.accum + c, (double)s);
-                        if (a.energy_out) a.energy_out[mm] = s;
-                    }
-                }
-                __syncthreads();
+            if (ms8) {
+                red[(2 * q) * 128 + tid] = e0;
+                red[(2 * q + 1) * 128 + tid] = e1;
             } else {
-                if (lane_valid) {
-                    int c = m % a.c_count;
-                    atomicAdd(a.accum + c, (double)energy);
-                    if (a.energy_out) a.energy_out[m] = energy;
-                }
-                __syncthreads();
+                red[q * 128 + tid] = e0 + e1;
             }
         }
+        tc_fence_before_sync();
+        __syncthreads();
+        {
+            // TPM threads per map, fixed summation order -> bit-reproducible per-map energy
+            const uint32_t t = tid / a.TPM, sub = tid % a.TPM;
+            float s = 0.f;
+            const bool live = (int)t < maps_here;
+            if (live) {
+                uint32_t g = a.div_j.div(t), j = t - g * a.J;
+                const float* rp = red + j * 128 + g * a.Ms;
+                for (uint32_t v = sub; v < (uint32_t)a.N; v += a.TPM) s += rp[v];
+            }
+            for (uint32_t o = a.TPM >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (live && sub == 0) {
+                int mm = map0 + (int)t;
+                int c = mm % a.c_count;
+                atomicAdd(a.accum + c, (double)s);
+                if (a.energy_out) a.energy_out[mm] = s;
+            }
+        }
+        __syncthreads();
     }
 
+    if (!alive && tid == 0) atomicExch(a.status, DCTP_DEV_MMA_TIMEOUT);
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<S::TMEM_COLS>(tmem);

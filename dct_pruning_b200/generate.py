@@ -1,0 +1,103 @@
+"""Importance generation: the drop-in for `imp_score(net, args)` and its batch drivers.
+
+    imp_score          /root/reference/utils/common.py:367-980  (site enumeration, np.save naming)
+    inference          /root/reference/utils/common.py:312-320
+    u2netp_inference   /root/reference/utils/common.py:323-332
+    CLI                /root/reference/importance_generation.py:8-61
+
+Output is byte-compatible with what the reference's prune_* scripts np.load:
+``importance_score/<net>_limit<N>/<stem>.npy``, .npy v1.0, '<f4', shape (C,).
+
+Multi-GPU: launched under torchrun (one process per GPU) every rank scores its own slice of
+every batch; the per-layer score sums meet in ONE NCCL all-reduce of the flat fp64 buffer at
+the end of the run, rank 0 writes the files.  The result does not depend on the rank count
+beyond fp64 summation order.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .hooks import ScoreSession
+from .sites import score_dir
+from .zoo import NET_INPUT
+
+
+def synthetic_batches(batch_size, side, limit, seed_base=1000, as_dict=False):
+    """Seeded stand-in for the reference loaders (datasets are unavailable offline): batch b is
+    randn(B,3,S,S) under manual_seed(seed_base + b) on the CPU generator, so CPU oracle and GPU path
+    see identical inputs.  `as_dict` mimics the DUTS loader's {'image': ...} samples."""
+    for b in range(limit):
+        g = torch.Generator().manual_seed(seed_base + b)
+        x = torch.randn(batch_size, 3, side, side, generator=g)
+        yield {'image': x} if as_dict else (x, torch.zeros(batch_size, dtype=torch.long))
+
+
+def _images_of(sample):
+    if isinstance(sample, dict):
+        return sample['image'].type(torch.FloatTensor)       # common.py:329-330
+    if isinstance(sample, (tuple, list)):
+        return sample[0]
+    return sample
+
+
+def rank_slice(n, rank, world):
+    """Contiguous share of an n-image batch for `rank` (ragged shards allowed, empty ones too)."""
+    lo = (n * rank) // world
+    hi = (n * (rank + 1)) // world
+    return lo, hi
+
+
+def inference(net, loader, limit, device, rank=0, world=1):
+    """eval + no_grad forward over the first `limit` batches (common.py:312-320); under
+    world > 1 each rank forwards its contiguous slice of every batch."""
+    net.eval()
+    n = 0
+    with torch.no_grad():
+        for batch_idx, sample in enumerate(loader):
+            if batch_idx >= limit:
+                break
+            x = _images_of(sample)
+            if world > 1:
+                lo, hi = rank_slice(x.shape[0], rank, world)
+                x = x[lo:hi]
+            if x.shape[0] == 0:
+                continue
+            n += x.shape[0]
+            net(x.to(device, non_blocking=True))
+    return n
+
+
+def imp_score(net, args, loader=None, out_root='importance_score', write=True, path='auto'):
+    """Score every hook site of `net` over `args.limit` batches and write the reference's files.
+
+    args: namespace with .net, .limit, .batch_size (and optionally .seed_base).  Returns
+    {file_stem: float32 vector}.  The net must already live on a CUDA device."""
+    import torch.distributed as dist
+    device = next(net.parameters()).device
+    if device.type != 'cuda':
+        raise RuntimeError('imp_score needs the net on a CUDA device (got %s); there is no CPU fallback' % device)
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    if loader is None:
+        _, side = NET_INPUT[args.net]
+        side = getattr(args, 'input_side', None) or side
+        loader = synthetic_batches(args.batch_size, side, args.limit,
+                                   seed_base=getattr(args, 'seed_base', 1000), as_dict=(args.net == 'u2netp'))
+    session = ScoreSession(net, args.net, path=path)
+    with session:
+        inference(net, loader, args.limit, device, rank=rank, world=world)
+    files = session.finalize()
+    if write and rank == 0:
+        write_score_files(files, score_dir(args.net, args.limit, out_root))
+    if world > 1:
+        dist.barrier()
+    return files
+
+
+def write_score_files(files, directory):
+    os.makedirs(directory, exist_ok=True)
+    for stem, vec in files.items():
+        np.save(os.path.join(directory, stem + '.npy'), np.ascontiguousarray(vec, dtype=np.float32))
+        print(os.path.join(directory, stem) + ':done!')       # common.py:395
+    return directory

@@ -1,0 +1,170 @@
+"""Forward-hook side of the scoring path: every hook site of a net live at once.
+
+Replaces the three hook functions and their module-global accumulators in
+/root/reference/utils/common.py:
+
+    get_feature_hook              :262-277   'O'  all channels of the module output
+    get_feature_hook_densenet     :280-293   'D'  last 12 channels of the output
+    get_feature_hook_u2net_input  :296-309   'I'  all channels of input[0]
+    feature_result / total        :258-259   ->   one flat fp64 device accumulator per session
+
+Each hook call is one asynchronous `dctp_score_accum` launch on the current torch stream:
+the activation is read once where cuDNN left it (NCHW fp32, any batch/channel stride), no
+coefficient tensor or per-slice value ever reaches host memory, and nothing synchronises
+until `finalize()`.  The reference runs one forward sweep per site; registering all sites
+together gives the same numbers on fixed inputs with one forward per batch.
+
+There is no CPU path: a hook fired on a CPU tensor raises.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .sites import DENSENET_WINDOW, VARIANT_INPUT, VARIANT_LAST12, hook_sites, resolve_module
+
+
+class ScoreSession:
+    def __init__(self, net, net_name, path='auto', capacity=1 << 18, sites=None):
+        self.net = net
+        self.net_name = net_name
+        self.sites = list(hook_sites(net_name, net) if sites is None else sites)
+        self.path = _lib.PATHS[path] if isinstance(path, str) else int(path)
+        self.capacity = capacity
+        self.flat = None                      # fp64 [capacity + 1]; last used slot (+1) carries the image count
+        self.used = 0
+        self.slots = [None] * len(self.sites)  # (offset, channels scored)
+        self.images = [0] * len(self.sites)
+        self.handles = []
+        self.lib = _lib.load()
+        self.launches = 0
+
+    # ------------------------------------------------------------------ registration
+    def register(self):
+        if self.handles:
+            raise RuntimeError('hooks already registered')
+        for idx, site in enumerate(self.sites):
+            module = resolve_module(self.net, site.module)
+            self.handles.append(module.register_forward_hook(self._make_hook(idx, site)))
+        return self
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+
+    def __enter__(self):
+        return self.register()
+
+    def __exit__(self, *exc):
+        self.remove()
+
+    def _make_hook(self, idx, site):
+        take_input = site.variant == VARIANT_INPUT
+
+        def hook(module, inputs, output):
+            self.score(idx, inputs[0] if take_input else output)
+        return hook
+
+    # ------------------------------------------------------------------ one hook firing
+    def score(self, idx, t):
+        if not t.is_cuda:
+            raise RuntimeError('dct_pruning_b200 scores on CUDA only (site %r fired on %s); there is no CPU fallback'
+                               % (self.sites[idx].module, t.device))
+        if t.dim() != 4:
+            raise ValueError('site %r: expected an NCHW activation, got shape %s' % (self.sites[idx].module, tuple(t.shape)))
+        if t.dtype != torch.float32:
+            t = t.float()                     # the reference scores in fp32 (common.py:233,289)
+        if t.stride(3) != 1 or t.stride(2) < t.shape[3]:
+            t = t.contiguous()
+        B, C, H, W = t.shape
+        if self.sites[idx].variant == VARIANT_LAST12:
+            if C < DENSENET_WINDOW:
+                raise ValueError('site %r: DenseNet window needs >= %d channels, got %d'
+                                 % (self.sites[idx].module, DENSENET_WINDOW, C))
+            c_begin, c_count = C - DENSENET_WINDOW, DENSENET_WINDOW
+        else:
+            c_begin, c_count = 0, C
+        off = self._slot(idx, c_count, t.device)
+        acc = self.flat[off:off + c_count]
+        _lib.check(self.lib.dctp_score_accum(_lib.ptr(t), B, H, W, t.stride(0), t.stride(1), t.stride(2),
+                                             c_begin, c_count, _lib.ptr(acc), None, None,
+                                             self.path, _lib.current_stream()))
+        self.images[idx] += B
+        self.launches += 1
+
+    def _slot(self, idx, c_count, device):
+        if self.flat is None:
+            with torch.cuda.device(device):
+                _lib.check(self.lib.dctp_init())
+            self.flat = torch.zeros(self.capacity + 1, dtype=torch.float64, device=device)
+        slot = self.slots[idx]
+        if slot is None:
+            if self.used + c_count > self.capacity:
+                raise RuntimeError('score accumulator capacity %d exceeded' % self.capacity)
+            slot = self.slots[idx] = (self.used, c_count)
+            self.used += c_count
+        elif slot[1] != c_count:
+            raise ValueError('site %r changed width: %d -> %d channels' % (self.sites[idx].module, slot[1], c_count))
+        return slot[0]
+
+    def prepare(self, sides):
+        """Upload the cosine bases for the given map sides ahead of time (keeps hooks capture-safe)."""
+        for s in sides:
+            h, w = (s, s) if isinstance(s, int) else s
+            _lib.check(self.lib.dctp_prepare(h, w))
+
+    def reset(self):
+        """Start a new run (the reference's reset of feature_result/total, common.py:396-397)."""
+        if self.flat is not None:
+            self.flat.zero_()
+        self.images = [0] * len(self.sites)
+
+    # ------------------------------------------------------------------ end of run
+    def finalize(self, group=None, check=True):
+        """Sum over ranks (one all-reduce of the flat buffer), divide by the image count, cast to
+        fp32.  Returns {file_stem: float32 numpy vector}, the payload of the reference's np.save calls."""
+        device_scores = self.finalize_device(group=group, check=check)
+        host = device_scores.cpu().numpy()
+        return self.split_files(host)
+
+    def finalize_device(self, group=None, check=True):
+        fired = [n for n, s in zip(self.images, self.slots) if s is not None]
+        if self.flat is None or not fired:
+            raise RuntimeError('no hook fired: nothing to finalize')
+        if len(set(fired)) != 1:
+            raise RuntimeError('hook sites saw different image counts: %s' % sorted(set(fired)))
+        n = self.used
+        self.flat[n] = float(fired[0])
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat[:n + 1], op=dist.ReduceOp.SUM, group=group)
+            n_images = float(self.flat[n].item())
+        else:
+            n_images = float(fired[0])
+        self.n_images = n_images
+        out = torch.empty(n, dtype=torch.float32, device=self.flat.device)
+        _lib.check(self.lib.dctp_finalize(_lib.ptr(self.flat), n_images, _lib.ptr(out), n, _lib.current_stream()))
+        if check:
+            _lib.check(self.lib.dctp_check(_lib.current_stream()))
+        return out
+
+    def split_files(self, host_scores):
+        files = {}
+        for site, slot in zip(self.sites, self.slots):
+            if slot is None:
+                continue
+            vec = host_scores[slot[0]:slot[0] + slot[1]]
+            for f in site.files:
+                files[f.stem] = np.array(vec if f.lo is None else vec[f.lo:f.hi], dtype=np.float32, copy=True)
+        return files
+
+    def file_segments(self):
+        """[(file_stem, offset into the flat score vector, length)] in site order."""
+        segs = []
+        for site, slot in zip(self.sites, self.slots):
+            if slot is None:
+                continue
+            for f in site.files:
+                lo, hi = (0, slot[1]) if f.lo is None else (f.lo, f.hi)
+                segs.append((f.stem, slot[0] + lo, hi - lo))
+        return segs

@@ -1,0 +1,103 @@
+/* dctp.h - C ABI of libdctp.so: the B200 (sm_100a) DCT importance-score path.
+ *
+ * Drop-in boundary for the importance-generation hot path of semchan/DCT_Pruning.  The reference
+ * has no native layer; each entry point below names the Python it replaces (file:line under
+ * /root/reference).  A maintainer binds these with ctypes; the shipped Python
+ * host side (dct_pruning_b200/_lib.py) does exactly that.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `stream` is a cudaStream_t passed as void* (0 = default stream)
+ *   - pointers named x / accum / scores / out ... are DEVICE pointers owned by the caller unless the
+ *     name ends in _host; the library allocates only its cached cosine bases, a status word and the
+ *     scratch of the *_host convenience entry, all released by dctp_shutdown()
+ *   - return value: 0 on success, a negative DCTP_E_* code otherwise; dctp_last_error() gives the text
+ *   - no C++ exception crosses the boundary, nothing calls exit(), there is NO CPU fallback:
+ *     without a CUDA device every compute entry returns DCTP_E_CUDA
+ *   - one host thread per process drives the library (forward hooks fire on the forward thread);
+ *     calls are asynchronous on `stream` unless stated otherwise
+ */
+#ifndef DCTP_H
+#define DCTP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCTP_VERSION 100          /* 0.1.0 */
+
+#define DCTP_OK            0
+#define DCTP_E_INVALID    -1      /* bad argument (null pointer, non-positive size, window out of range) */
+#define DCTP_E_CUDA       -2      /* CUDA runtime error; text in dctp_last_error() */
+#define DCTP_E_UNSUPPORTED -3     /* shape / layout the requested kernel path does not take */
+#define DCTP_E_DEVICE     -4      /* a kernel reported a fault in the device status word (tensor-core wait timed out) */
+
+/* kernel path for dctp_score_accum */
+#define DCTP_PATH_AUTO   0        /* tensor cores when the shape allows, CUDA cores otherwise */
+#define DCTP_PATH_UMMA   1        /* tcgen05/TMEM bf16x3 kernel; square maps, side <= 128, contiguous maps */
+#define DCTP_PATH_SIMT   2        /* fp32 CUDA-core kernels; any H x W, strided rows */
+
+int dctp_version(void);
+const char* dctp_last_error(void);
+
+/* Bind to the current CUDA device, set kernel attributes, allocate the status word.  Idempotent. */
+int dctp_init(void);
+/* Free every cached basis / scratch buffer.  The library can be re-initialised afterwards. */
+int dctp_shutdown(void);
+
+/* Build and upload the cosine bases an H x W map needs (synchronous, cached per size).  Called
+ * implicitly by dctp_score_accum on first use of a size; call it ahead of time when the scoring
+ * calls must stay asynchronous / CUDA-graph capturable. */
+int dctp_prepare(int H, int W);
+
+/* Fused hook kernel.  Replaces get_feature_hook / get_feature_hook_densenet /
+ * get_feature_hook_u2net_input (utils/common.py:262-277, :280-293, :296-309) up to the per-channel
+ * batch sum `c.view(a,-1).sum(0)` (:273-274):
+ *
+ *   accum[j] += sum_{b < B} sum_{u,v} DCT2_ortho(x[b, c_begin + j])[u,v]^2        j in [0, c_count)
+ *
+ * x           fp32 activation, element (b, c, h, w) at x[b*stride_b + c*stride_c + h*stride_h + w]
+ *             (strides in elements, innermost stride 1)
+ * c_begin/c_count  scored channel window (DenseNet variant: the last 12 channels, common.py:285)
+ * accum       fp64 [c_count], caller-zeroed before the first batch, accumulated across calls
+ * energy_out  optional fp32 [B * c_count]: per-(image, channel) energies, image-major (may be NULL)
+ * coeff_out   optional fp32 [B * c_count * H * W]: the DCT coefficients themselves (debug / parity; NULL in production)
+ * path        DCTP_PATH_* */
+int dctp_score_accum(const float* x, int B, int H, int W,
+                     long long stride_b, long long stride_c, long long stride_h,
+                     int c_begin, int c_count,
+                     double* accum, float* energy_out, float* coeff_out,
+                     int path, void* stream);
+
+/* out[i] = (float)(accum[i] / n_images).  Replaces the running mean over images
+ * (utils/common.py:275-277) and the fp32 vector np.save writes (:394). */
+int dctp_finalize(const double* accum, double n_images, float* out, int n, void* stream);
+
+/* Segmented top-k: for segment s, scores[seg_offsets[s] .. seg_offsets[s+1]) are one layer's channel
+ * scores; writes the seg_k[s] kept channel ids (relative to the segment, ascending, int64) at
+ * out_idx[out_offsets[s] ...].  Replaces `np.argsort(imp)[C-k:]` + `.sort()`
+ * (utils/load_models.py:39-41, :102-104, :265-267, :313-315, :352-354, :407-409, :469-471, :521-523,
+ * :629-631 ... :746-748) with the stable tie rule (ties at the cut keep the highest channel ids).
+ * All four index arrays are device pointers; seg_offsets / out_offsets have n_seg + 1 entries. */
+int dctp_topk_segmented(const float* scores, const int* seg_offsets, const int* seg_k, int n_seg,
+                        long long* out_idx, const int* out_offsets, void* stream);
+
+/* Synchronise `stream` and report the device status word (DCTP_OK or DCTP_E_DEVICE); clears it. */
+int dctp_check(void* stream);
+
+/* Host-buffer convenience: score one activation that lives in HOST memory.  Copies x_host
+ * (contiguous [B, C, H, W] fp32) to the device, scores channels [c_begin, c_begin + c_count),
+ * divides by B and writes fp32 scores_host[c_count].  Synchronous.  This is the whole of
+ * get_feature_hook for one batch behind one call, for callers without a device tensor. */
+int dctp_score_host(const float* x_host, int B, int C, int H, int W, int c_begin, int c_count,
+                    float* scores_host, int path);
+
+/* Introspection for tests and benchmarks: which kernel path AUTO picks for a shape (DCTP_PATH_*),
+ * the number of kernel launches issued by this library since dctp_init(), SM count of the device. */
+int dctp_path_for(int H, int W, long long stride_h);
+long long dctp_launch_count(void);
+int dctp_sm_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCTP_H */
