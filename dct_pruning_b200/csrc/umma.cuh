@@ -37,13 +37,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a descriptor or pipeline bug must not hang the GPU.  try_wait itself sleeps in
-// hardware for a bounded time, so ~2^22 failed probes is seconds, far beyond any legitimate wait.
-// Returns false on timeout (the caller records it in the status word and carries on to the exit path).
+// Bounded wait: a descriptor or pipeline bug must not hang the GPU.  Legitimate waits are microseconds;
+// after 2 s of wall clock (%globaltimer) the wait gives up and returns false (the caller records it in
+// the status word and carries on to the exit path).
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin)
-        if (mbar_try_wait(bar, parity)) return true;
-    return false;
+    if (mbar_try_wait(bar, parity)) return true;
+    const uint64_t t0 = global_ns();
+#pragma unroll 1
+    for (;;) {
+#pragma unroll 1
+        for (int spin = 0; spin < 64; ++spin)
+            if (mbar_try_wait(bar, parity)) return true;
+        if (global_ns() - t0 > 2000000000ull) return false;
+    }
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

@@ -31,3 +31,11 @@ def init_from_env(backend=None):
 def shutdown():
     if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()
+
+
+def allreduce_sums(flat, group=None):
+    """Sum the flat per-layer score buffer (last entry = image count) over all ranks, in place.
+    The only collective of the scoring path; a no-op in a single process."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat

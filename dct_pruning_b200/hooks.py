@@ -135,12 +135,9 @@ class ScoreSession:
             raise RuntimeError('hook sites saw different image counts: %s' % sorted(set(fired)))
         n = self.used
         self.flat[n] = float(fired[0])
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat[:n + 1], op=dist.ReduceOp.SUM, group=group)
-            n_images = float(self.flat[n].item())
-        else:
-            n_images = float(fired[0])
+        from .dist import allreduce_sums
+        allreduce_sums(self.flat[:n + 1], group=group)        # one collective per run; no-op single process
+        n_images = float(self.flat[n].item())
         self.n_images = n_images
         out = torch.empty(n, dtype=torch.float32, device=self.flat.device)
         _lib.check(self.lib.dctp_finalize(_lib.ptr(self.flat), n_images, _lib.ptr(out), n, _lib.current_stream()))
