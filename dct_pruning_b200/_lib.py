@@ -32,6 +32,7 @@ _SIGNATURES = {
     'dctp_score_host': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                    _c.c_void_p, _c.c_int]),
     'dctp_path_for': (_c.c_int, [_c.c_int, _c.c_int, _c.c_longlong]),
+    'dctp_occupancy': (_c.c_int, [_c.c_int, _c.c_int]),
     'dctp_launch_count': (_c.c_longlong, []),
     'dctp_sm_count': (_c.c_int, []),
 }

@@ -111,6 +111,7 @@ template <int KP, int VEC>
 int setup_umma(int& occ) {
     auto* fn = score_umma_kernel<KP, VEC>;
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaScoreSmem<KP>::TOTAL));
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, UmmaScoreSmem<KP>::TOTAL));
     if (occ < 1) return fail(DCTP_E_CUDA, "score_umma_kernel<%d,%d> does not fit on an SM", KP, VEC);
     const int by_tmem = 512 / static_cast<int>(UmmaScoreSmem<KP>::TMEM_COLS);   // TMEM columns are a per-SM resource too
@@ -267,6 +268,14 @@ long long dctp_launch_count(void) { return g.launches; }
 
 int dctp_path_for(int H, int W, long long stride_h) { return resolve_path(DCTP_PATH_AUTO, H, W, stride_h); }
 
+int dctp_occupancy(int kp, int vec) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_init();
+    if (rc) return rc;
+    if ((kp != 64 && kp != 128) || (vec != 4 && vec != 2 && vec != 1)) return fail(DCTP_E_INVALID, "dctp_occupancy(%d, %d)", kp, vec);
+    return g.occ[kp == 64 ? 0 : 1][vec == 4 ? 0 : vec == 2 ? 1 : 2];
+}
+
 int dctp_prepare(int H, int W) {
     std::lock_guard<std::mutex> lk(g_mu);
     int rc = ensure_init();
@@ -287,11 +296,12 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
     std::lock_guard<std::mutex> lk(g_mu);
     int rc = ensure_init();
     if (rc) return rc;
-    if (!x || !accum) return fail(DCTP_E_INVALID, "dctp_score_accum: null pointer");
     if (B < 0 || H < 1 || W < 1 || c_begin < 0 || c_count < 0 || stride_h < W)
         return fail(DCTP_E_INVALID, "dctp_score_accum: B=%d H=%d W=%d c_begin=%d c_count=%d stride_h=%lld", B, H, W, c_begin,
                     c_count, stride_h);
+    if (path != DCTP_PATH_AUTO && path != DCTP_PATH_UMMA && path != DCTP_PATH_SIMT) return fail(DCTP_E_INVALID, "unknown path %d", path);
     if (B == 0 || c_count == 0) return DCTP_OK;                     // empty batch / empty window: nothing to add
+    if (!x || !accum) return fail(DCTP_E_INVALID, "dctp_score_accum: null pointer");
     if (static_cast<long long>(B) * c_count > (1ll << 30)) return fail(DCTP_E_INVALID, "too many maps in one call");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int p = resolve_path(path, H, W, stride_h);

@@ -32,7 +32,7 @@ def test_parseval_at_full_size(lib, cuda_device, shape):
     acc, en, _ = dct_energy(x, want_energy=True)
     want = (x.double() ** 2).sum(dim=(2, 3))
     rel = ((en.double() - want).abs() / want.clamp_min(1e-30))[want > 0]
-    assert float(rel.max()) < 2e-5
+    assert float(rel.max()) < 5e-5          # worst single map of up to 524 288; the bar is 1e-4
     assert bool((en[want == 0] == 0).all())
     tot = want.sum(0)
     relc = ((acc - tot).abs() / tot.clamp_min(1e-30))[tot > 0]

@@ -35,8 +35,14 @@ def generate(tag, device, path='auto'):
     return want, got
 
 
+FORWARD_NOISE_TOL = 5e-4     # cuDNN vs the reference's CPU convolutions, NOT the scoring kernels (see the strict test below)
+
+
 @pytest.mark.parametrize('tag', CASES)
-def test_scores_match_reference(lib, cuda_device, tag):
+def test_scores_match_reference_end_to_end(lib, cuda_device, tag):
+    """Whole pipeline on the GPU (cuDNN forward included) vs the files the reference wrote.  The forward
+    passes differ in summation order, which moves weak channels by a few 1e-4 relative; strong channels
+    (>= 1% of the layer's largest score) still meet the 1e-4 bar."""
     want, got = generate(tag, cuda_device)
     assert sorted(want) == sorted(got)
     flipped = total = 0
@@ -44,14 +50,60 @@ def test_scores_match_reference(lib, cuda_device, tag):
         w, g = want[stem].astype(np.float64), got[stem].astype(np.float64)
         assert g.shape == w.shape and got[stem].dtype == np.float32
         scale = max(w.max(), 1e-30)
-        live = w > 1e-6 * scale                      # channels carrying real energy
-        rel = np.abs(g[live] - w[live]) / w[live]
-        assert rel.size == 0 or rel.max() < 1e-4, (stem, rel.max())
-        # (near-)dead channels: absolute agreement at the layer's scale; exact zeros counted
+        live = w > 1e-6 * scale
+        rel = np.abs(g - w) / np.maximum(w, 1e-30)
+        assert rel[live].max(initial=0) < FORWARD_NOISE_TOL, (stem, rel[live].max())
+        strong = w >= 1e-2 * scale
+        assert rel[strong].max(initial=0) < 1e-4, (stem, rel[strong].max())
         assert np.abs(g[~live] - w[~live]).max(initial=0) < 1e-6 * scale + 1e-12, stem
         flipped += int(((w == 0) != (g == 0)).sum())
         total += w.size
     assert flipped <= max(1, total // 200), 'cuDNN vs CPU forward flipped %d of %d dead channels' % (flipped, total)
+
+
+STRICT = [('vgg_16_bn', 3, 32, 2), ('resnet_56', 2, 32, 1), ('densenet_40', 2, 32, 1), ('googlenet', 2, 32, 1),
+          ('resnet_50', 1, 64, 1), ('u2netp', 1, 32, 1)]
+
+
+@pytest.mark.parametrize('net_name,batch,side,limit', STRICT)
+def test_scores_match_oracle_on_identical_activations(lib, cuda_device, net_name, batch, side, limit):
+    """The north_star bar proper: the SAME hooked activations (one CPU forward on this box) go through the
+    op-for-op port of the reference hooks and through the CUDA kernels.  Every live channel within 1e-4,
+    every channel the reference scores as exactly 0 is exactly 0."""
+    from dct_pruning_b200.generate import synthetic_batches
+    from dct_pruning_b200.hooks import ScoreSession
+    from dct_pruning_b200.sites import VARIANT_INPUT, resolve_module
+    from dct_pruning_b200.zoo import get_network
+    from oracle import reference_port as port
+    torch.manual_seed(0)
+    net = get_network(net_name).eval()
+    session = ScoreSession(net, net_name)
+    states = [port.ScoreState() for _ in session.sites]
+    oracle_hooks = [port.HOOKS[s.variant](st) for s, st in zip(session.sites, states)]
+    handles = []
+    for idx, site in enumerate(session.sites):
+        def both(module, inputs, output, idx=idx, take_input=(site.variant == VARIANT_INPUT)):
+            t = inputs[0] if take_input else output
+            oracle_hooks[idx](module, inputs, output)                    # the reference's arithmetic, on the CPU
+            session.score(idx, t.to(cuda_device))                         # the product, on the same numbers
+        handles.append(resolve_module(net, site.module).register_forward_hook(both))
+    with torch.no_grad():
+        for x, _ in synthetic_batches(batch, side, limit):
+            net(x)
+    for h in handles:
+        h.remove()
+    got = session.finalize()
+    checked = 0
+    for site, st in zip(session.sites, states):
+        vec = st.feature_result.numpy().astype(np.float64)
+        for f in site.files:
+            w = vec if f.lo is None else vec[f.lo:f.hi]
+            g = got[f.stem].astype(np.float64)
+            assert (g[w == 0] == 0).all(), f.stem
+            rel = np.abs(g - w)[w > 0] / w[w > 0]
+            assert rel.max(initial=0) < 1e-4, (f.stem, rel.max())
+            checked += w.size
+    assert checked > 0
 
 
 def test_written_files_are_byte_compatible(lib, cuda_device, tmp_path):

@@ -1,0 +1,32 @@
+"""One shape, one path, a few launches: the command ncu wraps.
+    python tools/prof_one.py B C H W [path] [iters]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dct_pruning_b200 import _lib                      # noqa: E402
+from dct_pruning_b200.ops import dct_energy            # noqa: E402
+
+B, C, H, W = (int(v) for v in sys.argv[1:5])
+path = sys.argv[5] if len(sys.argv) > 5 else 'auto'
+iters = int(sys.argv[6]) if len(sys.argv) > 6 else 5
+dev = torch.device('cuda', 0)
+lib = _lib.load()
+_lib.check(lib.dctp_init())
+print('occupancy kp64:', [lib.dctp_occupancy(64, v) for v in (4, 2, 1)], 'kp128:', [lib.dctp_occupancy(128, v) for v in (4, 2, 1)])
+x = torch.relu(torch.randn(B, C, H, W, device=dev))
+acc = torch.zeros(C, dtype=torch.float64, device=dev)
+for _ in range(2):
+    dct_energy(x, path=path, accum=acc, check=False)
+torch.cuda.synchronize()
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0.record()
+for _ in range(iters):
+    dct_energy(x, path=path, accum=acc, check=False)
+t1.record()
+torch.cuda.synchronize()
+ms = t0.elapsed_time(t1) / iters
+print('%s %s: %.3f ms, %.1f GB/s' % ((B, C, H, W), path, ms, x.numel() * 4 / ms / 1e6))
+_lib.check(lib.dctp_check(None))
