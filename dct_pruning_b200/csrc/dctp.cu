@@ -40,6 +40,7 @@ struct SimtBasis { float* t = nullptr; };                               // [N x 
 struct State {
     bool ready = false;
     int device = -1, sm_count = 0;
+    size_t smem_per_sm = 0;
     int* status = nullptr;
     long long launches = 0;
     std::map<std::pair<int, int>, UmmaBasis> umma;     // (N, KP)
@@ -112,10 +113,19 @@ int setup_umma(int& occ) {
     auto* fn = score_umma_kernel<KP, VEC>;
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaScoreSmem<KP>::TOTAL));
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, UmmaScoreSmem<KP>::TOTAL));
-    if (occ < 1) return fail(DCTP_E_CUDA, "score_umma_kernel<%d,%d> does not fit on an SM", KP, VEC);
+    // Resident CTAs per SM from the kernel's own resources.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor
+    // answered 1 for this kernel on B200 / CUDA 12.9 although shared memory allows 4 and registers 5 - ncu's
+    // launch__occupancy_limit_* agree with the arithmetic below - so the grid is sized from first principles.)
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, fn));
+    const int by_smem = static_cast<int>(g.smem_per_sm / (UmmaScoreSmem<KP>::TOTAL + 1024));   // + driver-reserved KB per CTA
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 128;
+    const int by_regs = regs_per_cta > 0 ? 65536 / regs_per_cta : 1;
     const int by_tmem = 512 / static_cast<int>(UmmaScoreSmem<KP>::TMEM_COLS);   // TMEM columns are a per-SM resource too
+    occ = by_smem < by_regs ? by_smem : by_regs;
     if (occ > by_tmem) occ = by_tmem;
+    if (occ > 16) occ = 16;
+    if (occ < 1) return fail(DCTP_E_CUDA, "score_umma_kernel<%d,%d> does not fit on an SM", KP, VEC);
     return DCTP_OK;
 }
 
@@ -129,6 +139,7 @@ int ensure_init() {
         return fail(DCTP_E_UNSUPPORTED, "libdctp is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
     g.device = dev;
     g.sm_count = prop.multiProcessorCount;
+    g.smem_per_sm = prop.sharedMemPerMultiprocessor;
     int rc;
     if ((rc = setup_umma<64, 4>(g.occ[0][0]))) return rc;
     if ((rc = setup_umma<64, 2>(g.occ[0][1]))) return rc;

@@ -310,12 +310,21 @@ __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) 
                 uint32_t r[16];
                 tmem_ld16(tmem_lane + KP + q * a.N2 + c0, r);
                 tmem_ld_wait();
+                if (c0 + 16 <= col_lim) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {     // columns past the group's own map(s) hold leftovers: masked
-                    float z0 = c0 + i < col_lim ? __uint_as_float(r[i]) : 0.f;
-                    float z1 = c0 + 8 + i < col_lim ? __uint_as_float(r[8 + i]) : 0.f;
-                    e0 = fmaf(z0, z0, e0);
-                    e1 = fmaf(z1, z1, e1);
+                    for (int i = 0; i < 8; ++i) {
+                        float z0 = __uint_as_float(r[i]), z1 = __uint_as_float(r[8 + i]);
+                        e0 = fmaf(z0, z0, e0);
+                        e1 = fmaf(z1, z1, e1);
+                    }
+                } else {                          // columns past the group's own map(s) hold leftovers: masked
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float z0 = c0 + i < col_lim ? __uint_as_float(r[i]) : 0.f;
+                        float z1 = c0 + 8 + i < col_lim ? __uint_as_float(r[8 + i]) : 0.f;
+                        e0 = fmaf(z0, z0, e0);
+                        e1 = fmaf(z1, z1, e1);
+                    }
                 }
                 if (a.dump != nullptr && lane_in_map) {
 #pragma unroll
