@@ -34,7 +34,11 @@ int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(DCTP_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));       \
     } while (0)
 
-struct UmmaBasis { uint16_t *hi = nullptr, *lo = nullptr; };            // [KP x KP] block-diagonal I_J (x) C_N
+struct UmmaBasis {                                                       // per (N, KP)
+    uint16_t *hi = nullptr, *lo = nullptr;                               // [KP x KP] block-diagonal I_J (x) C_N
+    uint16_t* scatter = nullptr;                                         // [tile_vec][vpe] operand offsets of a dense tile (or null)
+    int vpe = 0, tile_vec = 0;
+};
 struct SimtBasis { float* t = nullptr; };                               // [N x N], t[n*N + k] = C_N[k][n]
 
 struct State {
@@ -45,7 +49,7 @@ struct State {
     long long launches = 0;
     std::map<std::pair<int, int>, UmmaBasis> umma;     // (N, KP)
     std::map<int, SimtBasis> simt;                     // N
-    int occ[2][3] = {{0, 0, 0}, {0, 0, 0}};            // resident CTAs/SM per (KP, VEC) instantiation
+    int regs[2][6] = {{0}, {0}};                       // registers/thread per (KP, load mode) instantiation
     // scratch of dctp_score_host (grow-only)
     float* hx = nullptr; size_t hx_bytes = 0;
     double* hacc = nullptr; float* hout = nullptr; size_t hc = 0;
@@ -88,6 +92,22 @@ int get_umma_basis(int N, int KP, UmmaBasis& out) {
     CUDA_TRY(cudaMalloc(&b.lo, lo.size() * 2));
     CUDA_TRY(cudaMemcpy(b.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(b.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    // scatter table of the dense load path: where element e of a full tile (maps back to back) lands in A1
+    const int G = 128 / Ms, MT = G * J, NN = N * N;
+    if ((MT * NN) % 4 == 0) {
+        b.vpe = (N % 4 == 0) ? 1 : (N % 2 == 0) ? 2 : 4;
+        b.tile_vec = MT * NN / 4;
+        const int step = 4 / b.vpe;
+        std::vector<uint16_t> tab(static_cast<size_t>(b.tile_vec) * b.vpe + 8, 0);
+        for (int v = 0; v < b.tile_vec; ++v)
+            for (int s = 0; s < b.vpe; ++s) {
+                const int e = 4 * v + s * step, t = e / NN, r = e % NN;
+                tab[(size_t)v * b.vpe + s] =
+                    static_cast<uint16_t>(detail::kmajor_off((t / J) * Ms + r / N, (t % J) * Ms + r % N, 128));
+            }
+        CUDA_TRY(cudaMalloc(&b.scatter, tab.size() * 2));
+        CUDA_TRY(cudaMemcpy(b.scatter, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice));
+    }
     g.umma[key] = b;
     out = b;
     return DCTP_OK;
@@ -108,25 +128,41 @@ int get_simt_basis(int N, SimtBasis& out) {
 }
 
 // ------------------------------------------------------------------ init
-template <int KP, int VEC>
-int setup_umma(int& occ) {
-    auto* fn = score_umma_kernel<KP, VEC>;
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaScoreSmem<KP>::TOTAL));
+template <int KP, int MODE>
+int setup_umma(int& regs) {
+    auto* fn = score_umma_kernel<KP, MODE>;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, KP == 64 ? 100 * 1024 : 200 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    // Resident CTAs per SM from the kernel's own resources.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor
-    // answered 1 for this kernel on B200 / CUDA 12.9 although shared memory allows 4 and registers 5 - ncu's
-    // launch__occupancy_limit_* agree with the arithmetic below - so the grid is sized from first principles.)
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, fn));
-    const int by_smem = static_cast<int>(g.smem_per_sm / (UmmaScoreSmem<KP>::TOTAL + 1024));   // + driver-reserved KB per CTA
-    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 128;
+    regs = fa.numRegs;
+    return DCTP_OK;
+}
+
+// Resident CTAs per SM from the kernel's own resources.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor
+// answered 1 for this kernel on B200 / CUDA 12.9 although shared memory allows 4 and registers 5 - ncu's
+// launch__occupancy_limit_* agree with the arithmetic below - so the grid is sized from first principles.)
+int umma_occupancy(int kp, int mode, size_t smem_bytes) {
+    const int regs = g.regs[kp == 64 ? 0 : 1][mode];
+    const int by_smem = static_cast<int>(g.smem_per_sm / (smem_bytes + 1024));       // + driver-reserved KB per CTA
+    const int regs_per_cta = ((regs + 7) / 8 * 8) * 128;
     const int by_regs = regs_per_cta > 0 ? 65536 / regs_per_cta : 1;
-    const int by_tmem = 512 / static_cast<int>(UmmaScoreSmem<KP>::TMEM_COLS);   // TMEM columns are a per-SM resource too
-    occ = by_smem < by_regs ? by_smem : by_regs;
+    const int by_tmem = 512 / (2 * kp);                                              // TMEM columns are a per-SM resource too
+    int occ = by_smem < by_regs ? by_smem : by_regs;
     if (occ > by_tmem) occ = by_tmem;
     if (occ > 16) occ = 16;
-    if (occ < 1) return fail(DCTP_E_CUDA, "score_umma_kernel<%d,%d> does not fit on an SM", KP, VEC);
-    return DCTP_OK;
+    return occ < 1 ? 1 : occ;
+}
+
+template <int KP>
+int setup_umma_all(int* regs) {
+    int rc;
+    if ((rc = setup_umma<KP, LOAD_DENSE1>(regs[LOAD_DENSE1]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_DENSE2>(regs[LOAD_DENSE2]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_DENSE4>(regs[LOAD_DENSE4]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_GEN4>(regs[LOAD_GEN4]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_GEN2>(regs[LOAD_GEN2]))) return rc;
+    return setup_umma<KP, LOAD_GEN1>(regs[LOAD_GEN1]);
 }
 
 int ensure_init() {
@@ -141,12 +177,8 @@ int ensure_init() {
     g.sm_count = prop.multiProcessorCount;
     g.smem_per_sm = prop.sharedMemPerMultiprocessor;
     int rc;
-    if ((rc = setup_umma<64, 4>(g.occ[0][0]))) return rc;
-    if ((rc = setup_umma<64, 2>(g.occ[0][1]))) return rc;
-    if ((rc = setup_umma<64, 1>(g.occ[0][2]))) return rc;
-    if ((rc = setup_umma<128, 4>(g.occ[1][0]))) return rc;
-    if ((rc = setup_umma<128, 2>(g.occ[1][1]))) return rc;
-    if ((rc = setup_umma<128, 1>(g.occ[1][2]))) return rc;
+    if ((rc = setup_umma_all<64>(g.regs[0]))) return rc;
+    if ((rc = setup_umma_all<128>(g.regs[1]))) return rc;
     CUDA_TRY(cudaFuncSetAttribute(score_simt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMALL_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(score_simt_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CUDA_TRY(cudaMalloc(&g.status, sizeof(int)));
@@ -193,17 +225,38 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
     a.TPM = pow2_floor(128 / a.MT < 32 ? 128 / a.MT : 32);
     a.idesc1 = umma::make_idesc_bf16(128, a.N1, false, false);
     a.idesc2 = umma::make_idesc_bf16(128, a.N2, true, false);
-    const int vec = pick_vec(x, stride_b, stride_c, c_begin, N);
-    a.div_vpm.set(a.NN / vec); a.div_n.set(N); a.div_ms.set(a.Ms); a.div_j.set(a.J);
     a.basis_hi = basis.hi; a.basis_lo = basis.lo;
     a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
-    const int kpi = KP == 64 ? 0 : 1, vi = vec == 4 ? 0 : vec == 2 ? 1 : 2;
-    int grid = g.sm_count * g.occ[kpi][vi];
+    a.div_n.set(N); a.div_ms.set(a.Ms); a.div_j.set(a.J);
+    // dense: every scored map back to back in memory (full channel range, packed strides), 16-B aligned
+    const float* first = x + static_cast<long long>(c_begin) * stride_c;
+    const bool dense = basis.scatter != nullptr && stride_c == a.NN && (B == 1 || stride_b == static_cast<long long>(c_count) * a.NN) &&
+                       (reinterpret_cast<uintptr_t>(first) % 16) == 0;
+    int mode;
+    if (dense) {
+        mode = basis.vpe == 1 ? LOAD_DENSE1 : basis.vpe == 2 ? LOAD_DENSE2 : LOAD_DENSE4;
+        a.x_dense = first; a.total_elems = static_cast<long long>(a.n_maps) * a.NN;
+        a.tile_vec = basis.tile_vec; a.scatter = basis.scatter;
+        a.var_bytes = static_cast<uint32_t>(basis.tile_vec) * basis.vpe * 2u;
+        a.div_vpm.set(1);
+    } else {
+        const int vec = pick_vec(x, stride_b, stride_c, c_begin, N);
+        mode = vec == 4 ? LOAD_GEN4 : vec == 2 ? LOAD_GEN2 : LOAD_GEN1;
+        a.var_bytes = 128 * sizeof(void*);
+        a.div_vpm.set(a.NN / vec);
+    }
+    a.red_bytes = static_cast<uint32_t>(a.J) * 512u;
+    const size_t smem = UmmaScoreSmem<KP>::total(a.red_bytes, a.var_bytes);
+    int grid = g.sm_count * umma_occupancy(KP, mode, smem);
     if (grid > a.num_tiles) grid = a.num_tiles;
-    const size_t smem = UmmaScoreSmem<KP>::TOTAL;
-    if (vec == 4) score_umma_kernel<KP, 4><<<grid, 128, smem, stream>>>(a);
-    else if (vec == 2) score_umma_kernel<KP, 2><<<grid, 128, smem, stream>>>(a);
-    else score_umma_kernel<KP, 1><<<grid, 128, smem, stream>>>(a);
+    switch (mode) {
+        case LOAD_DENSE1: score_umma_kernel<KP, LOAD_DENSE1><<<grid, 128, smem, stream>>>(a); break;
+        case LOAD_DENSE2: score_umma_kernel<KP, LOAD_DENSE2><<<grid, 128, smem, stream>>>(a); break;
+        case LOAD_DENSE4: score_umma_kernel<KP, LOAD_DENSE4><<<grid, 128, smem, stream>>>(a); break;
+        case LOAD_GEN4: score_umma_kernel<KP, LOAD_GEN4><<<grid, 128, smem, stream>>>(a); break;
+        case LOAD_GEN2: score_umma_kernel<KP, LOAD_GEN2><<<grid, 128, smem, stream>>>(a); break;
+        default: score_umma_kernel<KP, LOAD_GEN1><<<grid, 128, smem, stream>>>(a); break;
+    }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     return DCTP_OK;
@@ -262,7 +315,7 @@ int dctp_init(void) {
 int dctp_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g.ready) return DCTP_OK;
-    for (auto& kv : g.umma) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
+    for (auto& kv : g.umma) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); cudaFree(kv.second.scatter); }
     for (auto& kv : g.simt) cudaFree(kv.second.t);
     g.umma.clear(); g.simt.clear();
     cudaFree(g.status); cudaFree(g.hx); cudaFree(g.hacc); cudaFree(g.hout);
@@ -279,12 +332,13 @@ long long dctp_launch_count(void) { return g.launches; }
 
 int dctp_path_for(int H, int W, long long stride_h) { return resolve_path(DCTP_PATH_AUTO, H, W, stride_h); }
 
-int dctp_occupancy(int kp, int vec) {
+int dctp_occupancy(int kp, int mode) {
     std::lock_guard<std::mutex> lk(g_mu);
     int rc = ensure_init();
     if (rc) return rc;
-    if ((kp != 64 && kp != 128) || (vec != 4 && vec != 2 && vec != 1)) return fail(DCTP_E_INVALID, "dctp_occupancy(%d, %d)", kp, vec);
-    return g.occ[kp == 64 ? 0 : 1][vec == 4 ? 0 : vec == 2 ? 1 : 2];
+    if ((kp != 64 && kp != 128) || mode < 0 || mode > 5) return fail(DCTP_E_INVALID, "dctp_occupancy(%d, %d)", kp, mode);
+    const size_t smem = kp == 64 ? UmmaScoreSmem<64>::total(512, 3136) : UmmaScoreSmem<128>::total(512, 8192);
+    return umma_occupancy(kp, mode, smem);
 }
 
 int dctp_prepare(int H, int W) {

@@ -11,6 +11,7 @@
 //   Ms = N rounded up to 8            lanes (and contraction columns) one map occupies
 //   G  = 128 / Ms  lane groups,  J = KP / Ms  column groups,  map t of the tile sits at (g, j) = (t / J, t % J)
 //
+//   stage 0   HBM -> registers (128-bit loads, all of a tile's loads in flight at once) -> bf16 hi/lo -> A1
 //   stage 1   D1[(g,h), (j,v)] = sum_{(j',w)} A1[(g,h), (j',w)] * B[(j,v), (j',w)]
 //             A1[(g,h),(j,w)] = X_{g,j}[h,w]   K-major;  B = I_J (x) C_N  (block diagonal, zero padded)
 //             -> D1[(g,h),(j,v)] = Y_{g,j}[h,v] = (X C^T)[h,v]
@@ -22,8 +23,15 @@
 //
 // Every product runs as three bf16 MMAs: hi*hi + lo*hi + hi*lo (fp32 accumulate in TMEM).
 // Operands live in shared memory in the canonical SWIZZLE_128B layouts (8-row x 128-byte atoms).
-// A2 re-uses A1's storage (stage 1 has completed when epilogue 1 runs).  Positions of A1/A2 that
-// a tile does not write hold finite bf16 leftovers; they only ever meet zero entries of B.
+// A2 re-uses A1's storage (stage 1 has completed when epilogue 1 runs).  Positions of A1/A2 that a
+// tile does not write hold finite bf16 leftovers; they only ever meet zero entries of B.  (Nothing but
+// bf16 operand data may ever be stored there: an arbitrary bit pattern can read as NaN, and NaN * 0
+// would leak into live lanes.)
+//
+// Everything that is the same for every tile is computed once: the scatter table (where each loaded
+// vector lands in the swizzled operand: built on the host, staged into shared memory), the MMA
+// descriptor list, each lane's A2 store offsets.  Several CTAs share an SM (4 at KP = 64), so one
+// CTA's HBM round trip hides behind the others' tensor and epilogue phases.
 #pragma once
 #include "umma.cuh"
 
@@ -35,7 +43,17 @@ struct FastDiv {            // q = n / d for n < 2^32 / d
     __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : __umulhi(n, mul); }
 };
 
-enum : int { DCTP_DEV_OK = 0, DCTP_DEV_MMA_TIMEOUT = 1 };
+enum : int { DCTP_DEV_OK = 0, DCTP_DEV_MMA_TIMEOUT = 1, DCTP_DEV_SMEM_ALIGN = 2 };
+
+// how stage 0 reaches the maps
+enum : int {
+    LOAD_DENSE1 = 0,   // scored maps form one contiguous fp32 stream; N % 4 == 0: one 8-byte store per float4
+    LOAD_DENSE2 = 1,   //   "   N even: two 4-byte stores per float4
+    LOAD_DENSE4 = 2,   //   "   any N : four 2-byte stores per float4 (+ scalar tail)
+    LOAD_GEN4 = 3,     // per-map base pointers (channel windows, strided batches), 128-bit loads
+    LOAD_GEN2 = 4,     //   "   64-bit loads
+    LOAD_GEN1 = 5      //   "   32-bit loads
+};
 
 struct UmmaScoreArgs {
     const float* x;                 // activation base pointer (fp32, maps contiguous: stride_h = N, stride_w = 1)
@@ -52,6 +70,13 @@ struct UmmaScoreArgs {
     uint32_t idesc1, idesc2;
     uint32_t a2_lbo, a2_group_bytes;
     FastDiv div_vpm, div_n, div_ms, div_j;
+    // dense modes
+    const float* x_dense;           // first scored element (x + c_begin*stride_c)
+    long long total_elems;          // n_maps * NN
+    int tile_vec;                   // float4 vectors per full tile = MT*NN/4
+    const uint16_t* scatter;        // [tile_vec][vpe] byte offsets into the K-major A1 operand
+    uint32_t var_bytes;             // bytes of `scatter` (dense) / of the map-pointer array (generic)
+    uint32_t red_bytes;             // bytes of the epilogue-2 reduction scratch: J * 128 floats
     const uint16_t* basis_hi;       // [KP x KP] bf16 bits of I_J (x) C_N, row = output index, col = contraction index
     const uint16_t* basis_lo;
     double* accum;                  // [c_count] per-channel energy sums (fp64)
@@ -63,13 +88,19 @@ struct UmmaScoreArgs {
 namespace detail {
 
 // byte offset of bf16 element (row, k) in a K-major SWIZZLE_128B operand with `rows` rows
-__device__ __forceinline__ uint32_t kmajor_off(uint32_t row, uint32_t k, uint32_t rows) {
+__host__ __device__ __forceinline__ uint32_t kmajor_off(uint32_t row, uint32_t k, uint32_t rows) {
     uint32_t kb = k >> 6, kk = k & 63;
     return kb * (rows * 128u) + (row >> 3) * 1024u + (row & 7) * 128u + ((((kk >> 3) ^ row) & 7) << 4) + ((kk & 7) << 1);
 }
 // byte offset of bf16 element (m, k) in an MN-major SWIZZLE_128B operand; lbo = stride between 64-wide M blocks
 __device__ __forceinline__ uint32_t mnmajor_off(uint32_t m, uint32_t k, uint32_t lbo) {
     return (m >> 6) * lbo + (k >> 3) * 1024u + (k & 7) * 128u + (((((m & 63) >> 3) ^ k) & 7) << 4) + ((m & 7) << 1);
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
 
 template <int VEC> struct Ld;
@@ -109,7 +140,51 @@ template <> struct Ld<1> {
     }
 };
 
+// one float4 of the dense stream -> hi/lo operand bytes, scattered through the table entry
+template <int VPE> struct Scatter;
+template <> struct Scatter<1> {
+    using Entry = uint16_t;
+    __device__ static __forceinline__ void st(uint8_t* hi, uint8_t* lo, Entry e, const float4& v) {
+        uint32_t h0, l0, h1, l1;
+        umma::split2(v.x, v.y, h0, l0);
+        umma::split2(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint2*>(hi + e) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(lo + e) = make_uint2(l0, l1);
+    }
+};
+template <> struct Scatter<2> {
+    using Entry = uint32_t;        // two uint16 offsets
+    __device__ static __forceinline__ void st(uint8_t* hi, uint8_t* lo, Entry e, const float4& v) {
+        uint32_t h0, l0, h1, l1;
+        umma::split2(v.x, v.y, h0, l0);
+        umma::split2(v.z, v.w, h1, l1);
+        const uint32_t o0 = e & 0xFFFFu, o1 = e >> 16;
+        *reinterpret_cast<uint32_t*>(hi + o0) = h0;
+        *reinterpret_cast<uint32_t*>(lo + o0) = l0;
+        *reinterpret_cast<uint32_t*>(hi + o1) = h1;
+        *reinterpret_cast<uint32_t*>(lo + o1) = l1;
+    }
+};
+template <> struct Scatter<4> {
+    using Entry = uint2;           // four uint16 offsets
+    __device__ static __forceinline__ void st(uint8_t* hi, uint8_t* lo, Entry e, const float4& v) {
+        uint32_t h0, l0, h1, l1;
+        umma::split2(v.x, v.y, h0, l0);
+        umma::split2(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint16_t*>(hi + (e.x & 0xFFFFu)) = static_cast<uint16_t>(h0);
+        *reinterpret_cast<uint16_t*>(lo + (e.x & 0xFFFFu)) = static_cast<uint16_t>(l0);
+        *reinterpret_cast<uint16_t*>(hi + (e.x >> 16)) = static_cast<uint16_t>(h0 >> 16);
+        *reinterpret_cast<uint16_t*>(lo + (e.x >> 16)) = static_cast<uint16_t>(l0 >> 16);
+        *reinterpret_cast<uint16_t*>(hi + (e.y & 0xFFFFu)) = static_cast<uint16_t>(h1);
+        *reinterpret_cast<uint16_t*>(lo + (e.y & 0xFFFFu)) = static_cast<uint16_t>(l1);
+        *reinterpret_cast<uint16_t*>(hi + (e.y >> 16)) = static_cast<uint16_t>(h1 >> 16);
+        *reinterpret_cast<uint16_t*>(lo + (e.y >> 16)) = static_cast<uint16_t>(l1 >> 16);
+    }
+};
+
 }  // namespace detail
+
+constexpr uint32_t UMMA_MAX_MMAS = 48;      // 3 passes x (<= 8 k-steps) for each of the two stages
 
 template <int KP>
 struct UmmaScoreSmem {
@@ -121,31 +196,44 @@ struct UmmaScoreSmem {
     static constexpr uint32_t OFF_A_LO = OFF_A_HI + A_BYTES;
     static constexpr uint32_t OFF_B_HI = OFF_A_LO + A_BYTES;
     static constexpr uint32_t OFF_B_LO = OFF_B_HI + B_BYTES;
-    static constexpr uint32_t OFF_MISC = OFF_B_LO + B_BYTES;       // barrier, tmem slot, map pointers, reduction scratch
-    static constexpr uint32_t RED_FLOATS = 8 * 128;                // [J <= 8][128 lanes]
-    static constexpr uint32_t MISC_BYTES = 16 + 128 * 8 + RED_FLOATS * 4;
-    static constexpr uint32_t TOTAL = OFF_MISC + MISC_BYTES + 1024;  // + slack for manual 1024-B alignment
+    static constexpr uint32_t OFF_CTRL = OFF_B_LO + B_BYTES;       // mbarrier + TMEM slot
+    static constexpr uint32_t OFF_MMAS = OFF_CTRL + 64;            // precomputed MMA descriptor list
+    static constexpr uint32_t OFF_VAR = OFF_MMAS + UMMA_MAX_MMAS * 32;   // reduction scratch, then scatter table (dense) or map pointers (generic)
+    static constexpr uint32_t FIXED = OFF_VAR;
     static constexpr uint32_t TMEM_COLS = 2 * KP;                  // D1 | D2
+    __host__ __device__ static constexpr uint32_t total(uint32_t red_bytes, uint32_t var_bytes) {
+        return FIXED + red_bytes + ((var_bytes + 15u) & ~15u);
+    }
 };
 
-template <int KP, int VEC>
-__global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) {
+template <int KP, int MODE>
+__global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const UmmaScoreArgs a) {
     using S = UmmaScoreSmem<KP>;
     using namespace umma;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr bool DENSE = MODE <= LOAD_DENSE4;
+    constexpr int VPE = MODE == LOAD_DENSE1 ? 1 : MODE == LOAD_DENSE2 ? 2 : 4;
+    constexpr int VEC = MODE == LOAD_GEN4 ? 4 : MODE == LOAD_GEN2 ? 2 : 1;
+    constexpr int NCHUNK = KP / 8;                                 // 8-column chunks of a D1 row
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_hi = smem + S::OFF_A_HI;
     uint8_t* a_lo = smem + S::OFF_A_LO;
     uint8_t* b_hi = smem + S::OFF_B_HI;
     uint8_t* b_lo = smem + S::OFF_B_LO;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::OFF_MISC);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_MISC + 8);
-    const float** mptr = reinterpret_cast<const float**>(smem + S::OFF_MISC + 16);   // per-tile map base pointers
-    float* red = reinterpret_cast<float*>(smem + S::OFF_MISC + 16 + 128 * 8);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::OFF_CTRL);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_CTRL + 8);
+    uint4* mmas = reinterpret_cast<uint4*>(smem + S::OFF_MMAS);
+    float* red = reinterpret_cast<float*>(smem + S::OFF_VAR);     // epilogue-2 scratch, [J <= 8][128 lanes]
+    const float** mptr = reinterpret_cast<const float**>(smem + S::OFF_VAR + a.red_bytes);   // generic modes
+    const typename detail::Scatter<VPE>::Entry* scat =
+        reinterpret_cast<const typename detail::Scatter<VPE>::Entry*>(smem + S::OFF_VAR + a.red_bytes);  // dense modes
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    if ((smem_u32(smem) & 1023u) != 0) {                           // SWIZZLE_128B atoms need 1024-B alignment
+        if (tid == 0) atomicExch(a.status, DCTP_DEV_SMEM_ALIGN);
+        return;
+    }
 
-    // ---- one-time setup: zero the operand area, stage the basis, TMEM, barrier
+    // ---- one-time setup: zero the operand area, stage basis and scatter table, MMA list, TMEM, barrier
     for (uint32_t off = tid * 16; off < S::OFF_B_HI; off += 128 * 16)
         *reinterpret_cast<uint4*>(smem + off) = make_uint4(0, 0, 0, 0);
     for (uint32_t i = tid; i < KP * (KP / 8); i += 128) {
@@ -155,6 +243,35 @@ __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) 
         uint32_t off = detail::kmajor_off(n, c8 * 8, KP);
         *reinterpret_cast<uint4*>(b_hi + off) = vh;
         *reinterpret_cast<uint4*>(b_lo + off) = vl;
+    }
+    if constexpr (DENSE) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.scatter);
+        uint4* dst = reinterpret_cast<uint4*>(smem + S::OFF_VAR + a.red_bytes);
+        for (uint32_t i = tid; i < (a.var_bytes + 15) / 16; i += 128) dst[i] = src[i];
+    }
+    const uint32_t n_mma1 = 3u * a.K1, n_mma2 = 3u * a.NQ * a.K2S;
+    if (tid < n_mma1 + n_mma2) {
+        // entry = {A descriptor, B descriptor | TMEM column, accumulate flag, instruction descriptor}
+        uint64_t da, db;
+        uint32_t dcol, acc, idesc;
+        if (tid < n_mma1) {
+            const uint32_t pass = tid / a.K1, ks = tid - pass * a.K1;
+            const uint32_t a_off = (ks >> 2) * (128u * 128u) + (ks & 3) * 32u;
+            const uint32_t b_off = (ks >> 2) * (KP * 128u) + (ks & 3) * 32u;
+            da = make_smem_desc(smem_u32(pass == 1 ? a_lo : a_hi) + a_off, 16, 1024, SWIZZLE_128B);
+            db = make_smem_desc(smem_u32(pass == 2 ? b_lo : b_hi) + b_off, 16, 1024, SWIZZLE_128B);
+            dcol = 0; acc = tid != 0; idesc = a.idesc1;
+        } else {
+            const uint32_t i = tid - n_mma1, per_q = 3u * a.K2S;
+            const uint32_t q = i / per_q, r = i - q * per_q, pass = r / a.K2S, ks = r - pass * a.K2S;
+            const uint32_t b_off = (ks >> 2) * (KP * 128u) + (ks & 3) * 32u;
+            da = make_smem_desc(smem_u32(pass == 1 ? a_lo : a_hi) + q * a.a2_group_bytes + ks * 2048u, a.a2_lbo, 1024, SWIZZLE_128B);
+            db = make_smem_desc(smem_u32(pass == 2 ? b_lo : b_hi) + b_off, 16, 1024, SWIZZLE_128B);
+            dcol = KP + q * a.N2; acc = r != 0; idesc = a.idesc2;
+        }
+        mmas[2 * tid] = make_uint4(static_cast<uint32_t>(da), static_cast<uint32_t>(da >> 32), static_cast<uint32_t>(db),
+                                   static_cast<uint32_t>(db >> 32));
+        mmas[2 * tid + 1] = make_uint4(dcol, acc, idesc, 0);
     }
     if (warp == 0) tmem_alloc<S::TMEM_COLS>(tmem_slot);
     if (tid == 0) {
@@ -168,38 +285,80 @@ __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) 
     const uint32_t tmem = *tmem_slot;
     const uint32_t tmem_lane = tmem + ((warp * 32u) << 16);
 
-    const uint64_t d_a_hi = make_smem_desc(smem_u32(a_hi), 16, 1024, SWIZZLE_128B);
-    const uint64_t d_a_lo = make_smem_desc(smem_u32(a_lo), 16, 1024, SWIZZLE_128B);
-    const uint64_t d_b_hi = make_smem_desc(smem_u32(b_hi), 16, 1024, SWIZZLE_128B);
-    const uint64_t d_b_lo = make_smem_desc(smem_u32(b_lo), 16, 1024, SWIZZLE_128B);
-    const uint64_t d_a2_hi = make_smem_desc(smem_u32(a_hi), a.a2_lbo, 1024, SWIZZLE_128B);
-    const uint64_t d_a2_lo = make_smem_desc(smem_u32(a_lo), a.a2_lbo, 1024, SWIZZLE_128B);
-
-    // this thread's TMEM lane as (lane group, row in map)
+    // this thread's TMEM lane as (lane group, row in map), and where its D1 chunks go in A2
     const uint32_t my_g = a.div_ms.div(tid);
     const uint32_t my_r = tid - my_g * a.Ms;
     const bool lane_in_map = my_g < (uint32_t)a.G && my_r < (uint32_t)a.N;
-    const uint32_t vpm = a.NN / VEC;                 // vectors per map
     const uint32_t used_cols = a.J * a.Ms;
     const bool ms8 = a.Ms == 8;
     const uint32_t col_lim = ms8 ? 16u : (uint32_t)a.Ms;   // meaningful D2 columns per stage-2 group
+    const uint32_t blocks_per_q = a.N2 >> 4;               // x16 column blocks per stage-2 group
+    uint32_t a2off[NCHUNK];
+#pragma unroll
+    for (int ci = 0; ci < NCHUNK; ++ci) {
+        const uint32_t c = ci * 8;
+        const uint32_t j = a.div_ms.div(c), v0 = c - j * a.Ms;
+        const uint32_t q = ms8 ? (j >> 1) : j;
+        const uint32_t k = ms8 ? ((j & 1) * 8 + my_r) : my_r;
+        a2off[ci] = q * a.a2_group_bytes + detail::mnmajor_off(my_g * a.Ms + v0, k, a.a2_lbo);
+    }
     uint32_t phase = 0;
     bool alive = true;
+
+    auto issue = [&](uint32_t first, uint32_t count) {             // one thread: the precomputed MMA list
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (uint32_t i = first; i < first + count; ++i) {
+            const uint4 d = mmas[2 * i], m = mmas[2 * i + 1];
+            mma_bf16_ss(tmem + m.x, (static_cast<uint64_t>(d.y) << 32) | d.x, (static_cast<uint64_t>(d.w) << 32) | d.z, m.z, m.y);
+        }
+        mma_commit(bar);
+    };
 
     for (int tile = blockIdx.x; tile < a.num_tiles && alive; tile += gridDim.x) {
         const int map0 = tile * a.MT;
         const int maps_here = min(a.MT, a.n_maps - map0);
 
         // ---- stage 0: HBM -> registers -> bf16 hi/lo -> A1 (each scored map is read exactly once)
-        if ((int)tid < maps_here) {
-            int m = map0 + (int)tid;
-            int b = m / a.c_count, c = m - b * a.c_count;
-            mptr[tid] = a.x + b * a.stride_b + (long long)(a.c_begin + c) * a.stride_c;
-        }
-        __syncthreads();
-        {
+        if constexpr (DENSE) {
+            const long long elem0 = static_cast<long long>(map0) * a.NN;
+            const long long left = a.total_elems - elem0;
+            const uint32_t n_full = static_cast<uint32_t>(min(static_cast<long long>(a.tile_vec), left >> 2));
+            const float4* src = reinterpret_cast<const float4*>(a.x_dense + elem0);
+            constexpr int U = 8;                                   // 8 x 16 B in flight per thread; x 4 CTAs covers the HBM latency
+#pragma unroll 1
+            for (uint32_t base = tid; base < n_full; base += 128 * U) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (base + u * 128 < n_full) v[u] = detail::ldg_stream(src + base + u * 128);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (base + u * 128 < n_full) detail::Scatter<VPE>::st(a_hi, a_lo, scat[base + u * 128], v[u]);
+            }
+            if constexpr (VPE == 4) {                              // odd sizes: the stream may end inside a float4
+                const uint32_t tail = static_cast<uint32_t>(min(static_cast<long long>(a.tile_vec) * 4, left)) - n_full * 4;
+                if (tid < tail && n_full < (uint32_t)a.tile_vec) {
+                    const float x = a.x_dense[elem0 + n_full * 4 + tid];
+                    const uint2 e = scat[n_full];
+                    const uint32_t o = tid == 0 ? (e.x & 0xFFFFu) : tid == 1 ? (e.x >> 16) : (e.y & 0xFFFFu);
+                    uint32_t h, l;
+                    split2(x, 0.f, h, l);
+                    *reinterpret_cast<uint16_t*>(a_hi + o) = static_cast<uint16_t>(h);
+                    *reinterpret_cast<uint16_t*>(a_lo + o) = static_cast<uint16_t>(l);
+                }
+            }
+        } else {
+            if ((int)tid < maps_here) {
+                int m = map0 + (int)tid;
+                int b = m / a.c_count, c = m - b * a.c_count;
+                mptr[tid] = a.x + b * a.stride_b + (long long)(a.c_begin + c) * a.stride_c;
+            }
+            __syncthreads();
+            const uint32_t vpm = a.NN / VEC;             // vectors per map
             const uint32_t total = maps_here * vpm;
             constexpr int U = VEC == 4 ? 8 : 4;
+#pragma unroll 1
             for (uint32_t base = 0; base < total; base += 128 * U) {
                 float v[U][VEC];
                 uint32_t off[U];
@@ -226,48 +385,32 @@ __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) 
         __syncthreads();
 
         // ---- stage 1 MMA: D1 = A1 * B^T  (hi*hi + lo*hi + hi*lo)
-        if (tid == 0) {
-            tc_fence_after_sync();
-            uint32_t acc = 0;
-#pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint64_t da = pass == 1 ? d_a_lo : d_a_hi;
-                const uint64_t db = pass == 2 ? d_b_lo : d_b_hi;
-#pragma unroll 1
-                for (uint32_t ks = 0; ks < (uint32_t)a.K1; ++ks) {
-                    uint32_t a_off = (ks >> 2) * (128u * 128u) + (ks & 3) * 32u;
-                    uint32_t b_off = (ks >> 2) * (KP * 128u) + (ks & 3) * 32u;
-                    mma_bf16_ss(tmem, desc_advance(da, a_off), desc_advance(db, b_off), a.idesc1, acc);
-                    acc = 1;
-                }
-            }
-            mma_commit(bar);
-        }
+        if (tid == 0) issue(0, n_mma1);
         if (!mbar_wait(bar, phase)) alive = false;
         phase ^= 1;
         tc_fence_after_sync();
 
         // ---- epilogue 1: D1 row (g,h) -> bf16 hi/lo -> A2_q[(g, v), k]   (MN-major operand, aliases A1)
-#pragma unroll 1
-        for (uint32_t c0 = 0; c0 < (uint32_t)a.N1; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_lane + c0, r);
-            tmem_ld_wait();
-            if (lane_in_map) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    uint32_t c = c0 + 8 * i;
-                    if (c < used_cols) {
-                        uint32_t j = a.div_ms.div(c), v0 = c - j * a.Ms;
-                        uint32_t q = ms8 ? (j >> 1) : j;
-                        uint32_t k = ms8 ? ((j & 1) * 8 + my_r) : my_r;
-                        uint32_t h4[4], l4[4];
+        for (int part = 0; part < KP / 32; ++part) {               // 32 columns at a time keeps the register footprint small
+            if ((uint32_t)(part * 32) < (uint32_t)a.N1) {
+                uint32_t r[2][16];
+                tmem_ld16(tmem_lane + part * 32, r[0]);
+                if ((uint32_t)(part * 32 + 16) < (uint32_t)a.N1) tmem_ld16(tmem_lane + part * 32 + 16, r[1]);
+                tmem_ld_wait();
+                if (lane_in_map) {
 #pragma unroll
-                        for (int p = 0; p < 4; ++p)
-                            split2(__uint_as_float(r[8 * i + 2 * p]), __uint_as_float(r[8 * i + 2 * p + 1]), h4[p], l4[p]);
-                        uint32_t off = q * a.a2_group_bytes + detail::mnmajor_off(my_g * a.Ms + v0, k, a.a2_lbo);
-                        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-                        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+                    for (int ci = 0; ci < 4; ++ci) {
+                        if ((uint32_t)(part * 32 + ci * 8) < used_cols) {
+                            uint32_t h4[4], l4[4];
+#pragma unroll
+                            for (int p = 0; p < 4; ++p)
+                                split2(__uint_as_float(r[ci >> 1][(ci & 1) * 8 + 2 * p]),
+                                       __uint_as_float(r[ci >> 1][(ci & 1) * 8 + 2 * p + 1]), h4[p], l4[p]);
+                            const uint32_t off = a2off[part * 4 + ci];
+                            *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                            *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+                        }
                     }
                 }
             }
@@ -277,72 +420,71 @@ __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) 
         __syncthreads();
 
         // ---- stage 2 MMA: per column group, D2 = A2_q * C^T, contraction over the map's rows
-        if (tid == 0) {
-            tc_fence_after_sync();
-#pragma unroll 1
-            for (uint32_t q = 0; q < (uint32_t)a.NQ; ++q) {
-                uint32_t acc = 0;
-#pragma unroll 1
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint64_t da = desc_advance(pass == 1 ? d_a2_lo : d_a2_hi, q * a.a2_group_bytes);
-                    const uint64_t db = pass == 2 ? d_b_lo : d_b_hi;
-#pragma unroll 1
-                    for (uint32_t ks = 0; ks < (uint32_t)a.K2S; ++ks) {
-                        uint32_t b_off = (ks >> 2) * (KP * 128u) + (ks & 3) * 32u;
-                        mma_bf16_ss(tmem + KP + q * a.N2, desc_advance(da, ks * 2048u), desc_advance(db, b_off), a.idesc2,
-                                    acc);
-                        acc = 1;
-                    }
-                }
-            }
-            mma_commit(bar);
-        }
+        if (tid == 0) issue(n_mma1, n_mma2);
         if (!mbar_wait(bar, phase)) alive = false;
         phase ^= 1;
         tc_fence_after_sync();
 
         // ---- epilogue 2: coefficients -> energy, never leaving the SM.  Lane = (g, v); column = (q, n).
-#pragma unroll 1
-        for (uint32_t q = 0; q < (uint32_t)a.NQ; ++q) {
-            float e0 = 0.f, e1 = 0.f;
-#pragma unroll 1
-            for (uint32_t c0 = 0; c0 < (uint32_t)a.N2; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tmem_lane + KP + q * a.N2 + c0, r);
-                tmem_ld_wait();
-                if (c0 + 16 <= col_lim) {
+        {
+            const uint32_t n_blocks = a.NQ * blocks_per_q;         // x16 column blocks holding coefficients
+            float e_acc = 0.f;
+            uint32_t q = 0, in_q = 0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float z0 = __uint_as_float(r[i]), z1 = __uint_as_float(r[8 + i]);
-                        e0 = fmaf(z0, z0, e0);
-                        e1 = fmaf(z1, z1, e1);
-                    }
-                } else {                          // columns past the group's own map(s) hold leftovers: masked
+            for (int part = 0; part < KP / 32; ++part) {
+                if ((uint32_t)(part * 2) < n_blocks) {
+                    uint32_t r[2][16];
+                    tmem_ld16(tmem_lane + KP + part * 32, r[0]);
+                    if ((uint32_t)(part * 2 + 1) < n_blocks) tmem_ld16(tmem_lane + KP + part * 32 + 16, r[1]);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float z0 = c0 + i < col_lim ? __uint_as_float(r[i]) : 0.f;
-                        float z1 = c0 + 8 + i < col_lim ? __uint_as_float(r[8 + i]) : 0.f;
-                        e0 = fmaf(z0, z0, e0);
-                        e1 = fmaf(z1, z1, e1);
+                    for (int b = 0; b < 2; ++b) {
+                        if ((uint32_t)(part * 2 + b) < n_blocks) {
+                            const uint32_t c0 = in_q * 16;         // first column of this block inside its group
+                            float e0 = 0.f, e1 = 0.f;
+                            if (c0 + 16 <= col_lim) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    float z0 = __uint_as_float(r[b][i]), z1 = __uint_as_float(r[b][8 + i]);
+                                    e0 = fmaf(z0, z0, e0);
+                                    e1 = fmaf(z1, z1, e1);
+                                }
+                            } else {                               // columns past the group's own map hold leftovers: masked
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    float z0 = c0 + i < col_lim ? __uint_as_float(r[b][i]) : 0.f;
+                                    float z1 = c0 + 8 + i < col_lim ? __uint_as_float(r[b][8 + i]) : 0.f;
+                                    e0 = fmaf(z0, z0, e0);
+                                    e1 = fmaf(z1, z1, e1);
+                                }
+                            }
+                            if (a.dump != nullptr && lane_in_map) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    uint32_t n = c0 + i;
+                                    uint32_t j = ms8 ? (2 * q + (n >> 3)) : q;
+                                    uint32_t u = ms8 ? (n & 7) : n;
+                                    int t = (int)(my_g * a.J + j);
+                                    if (u < (uint32_t)a.N && j < (uint32_t)a.J && t < maps_here)
+                                        a.dump[(long long)(map0 + t) * a.NN + u * a.N + my_r] = __uint_as_float(r[b][i]);
+                                }
+                            }
+                            if (ms8) {
+                                red[(2 * q) * 128 + tid] = e0;
+                                red[(2 * q + 1) * 128 + tid] = e1;
+                                ++q;
+                            } else {
+                                e_acc += e0 + e1;
+                                if (++in_q == blocks_per_q) {
+                                    red[q * 128 + tid] = e_acc;
+                                    e_acc = 0.f;
+                                    in_q = 0;
+                                    ++q;
+                                }
+                            }
+                        }
                     }
                 }
-                if (a.dump != nullptr && lane_in_map) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        uint32_t n = c0 + i;
-                        uint32_t j = ms8 ? (2 * q + (n >> 3)) : q;
-                        uint32_t u = ms8 ? (n & 7) : n;
-                        int t = (int)(my_g * a.J + j);
-                        if (u < (uint32_t)a.N && j < (uint32_t)a.J && t < maps_here)
-                            a.dump[(long long)(map0 + t) * a.NN + u * a.N + my_r] = __uint_as_float(r[i]);
-                    }
-                }
-            }
-            if (ms8) {
-                red[(2 * q) * 128 + tid] = e0;
-                red[(2 * q + 1) * 128 + tid] = e1;
-            } else {
-                red[q * 128 + tid] = e0 + e1;
             }
         }
         tc_fence_before_sync();
@@ -365,7 +507,7 @@ __global__ void __launch_bounds__(128) score_umma_kernel(const UmmaScoreArgs a) 
                 if (a.energy_out) a.energy_out[mm] = s;
             }
         }
-        __syncthreads();
+        __syncthreads();          // `red` is rewritten by the next tile's epilogue
     }
 
     if (!alive && tid == 0) atomicExch(a.status, DCTP_DEV_MMA_TIMEOUT);

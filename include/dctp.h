@@ -94,8 +94,9 @@ int dctp_score_host(const float* x_host, int B, int C, int H, int W, int c_begin
 /* Introspection for tests and benchmarks: which kernel path AUTO picks for a shape (DCTP_PATH_*),
  * the number of kernel launches issued by this library since dctp_init(), SM count of the device. */
 int dctp_path_for(int H, int W, long long stride_h);
-/* resident CTAs per SM of the tensor-core kernel instantiation (kp in {64,128}, vec in {4,2,1}) */
-int dctp_occupancy(int kp, int vec);
+/* resident CTAs per SM of the tensor-core kernel instantiation (kp in {64,128}; load mode 0..5: dense
+ * 8/4/2-byte scatter, generic 128/64/32-bit loads) at a typical table size */
+int dctp_occupancy(int kp, int mode);
 long long dctp_launch_count(void);
 int dctp_sm_count(void);
 
