@@ -49,7 +49,7 @@ struct State {
     long long launches = 0;
     std::map<std::pair<int, int>, UmmaBasis> umma;     // (N, KP)
     std::map<int, SimtBasis> simt;                     // N
-    int regs[2][6] = {{0}, {0}};                       // registers/thread per (KP, load mode) instantiation
+    int regs[2][6][2] = {};                            // registers/thread per (KP, load mode, prefetch) instantiation
     // scratch of dctp_score_host (grow-only)
     float* hx = nullptr; size_t hx_bytes = 0;
     double* hacc = nullptr; float* hout = nullptr; size_t hc = 0;
@@ -128,9 +128,9 @@ int get_simt_basis(int N, SimtBasis& out) {
 }
 
 // ------------------------------------------------------------------ init
-template <int KP, int MODE>
+template <int KP, int MODE, bool PF>
 int setup_umma(int& regs) {
-    auto* fn = score_umma_kernel<KP, MODE>;
+    auto* fn = score_umma_kernel<KP, MODE, PF>;
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, KP == 64 ? 100 * 1024 : 200 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     cudaFuncAttributes fa;
@@ -142,8 +142,8 @@ int setup_umma(int& regs) {
 // Resident CTAs per SM from the kernel's own resources.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor
 // answered 1 for this kernel on B200 / CUDA 12.9 although shared memory allows 4 and registers 5 - ncu's
 // launch__occupancy_limit_* agree with the arithmetic below - so the grid is sized from first principles.)
-int umma_occupancy(int kp, int mode, size_t smem_bytes) {
-    const int regs = g.regs[kp == 64 ? 0 : 1][mode];
+int umma_occupancy(int kp, int mode, bool pf, size_t smem_bytes) {
+    const int regs = g.regs[kp == 64 ? 0 : 1][mode][pf ? 1 : 0];
     const int by_smem = static_cast<int>(g.smem_per_sm / (smem_bytes + 1024));       // + driver-reserved KB per CTA
     const int regs_per_cta = ((regs + 7) / 8 * 8) * 128;
     const int by_regs = regs_per_cta > 0 ? 65536 / regs_per_cta : 1;
@@ -155,14 +155,17 @@ int umma_occupancy(int kp, int mode, size_t smem_bytes) {
 }
 
 template <int KP>
-int setup_umma_all(int* regs) {
+int setup_umma_all(int (*regs)[2]) {
     int rc;
-    if ((rc = setup_umma<KP, LOAD_DENSE1>(regs[LOAD_DENSE1]))) return rc;
-    if ((rc = setup_umma<KP, LOAD_DENSE2>(regs[LOAD_DENSE2]))) return rc;
-    if ((rc = setup_umma<KP, LOAD_DENSE4>(regs[LOAD_DENSE4]))) return rc;
-    if ((rc = setup_umma<KP, LOAD_GEN4>(regs[LOAD_GEN4]))) return rc;
-    if ((rc = setup_umma<KP, LOAD_GEN2>(regs[LOAD_GEN2]))) return rc;
-    return setup_umma<KP, LOAD_GEN1>(regs[LOAD_GEN1]);
+    if ((rc = setup_umma<KP, LOAD_DENSE1, false>(regs[LOAD_DENSE1][0]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_DENSE2, false>(regs[LOAD_DENSE2][0]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_DENSE4, false>(regs[LOAD_DENSE4][0]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_DENSE1, true>(regs[LOAD_DENSE1][1]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_DENSE2, true>(regs[LOAD_DENSE2][1]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_DENSE4, true>(regs[LOAD_DENSE4][1]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_GEN4, false>(regs[LOAD_GEN4][0]))) return rc;
+    if ((rc = setup_umma<KP, LOAD_GEN2, false>(regs[LOAD_GEN2][0]))) return rc;
+    return setup_umma<KP, LOAD_GEN1, false>(regs[LOAD_GEN1][0]);
 }
 
 int ensure_init() {
@@ -245,17 +248,27 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
         a.var_bytes = 128 * sizeof(void*);
         a.div_vpm.set(a.NN / vec);
     }
-    a.red_bytes = static_cast<uint32_t>(a.J) * 512u;
+    a.red_bytes = (a.Ms == 8 ? 8u : static_cast<uint32_t>(a.NQ * (a.N2 / 16))) * 512u;
+    const bool pf = dense && basis.tile_vec <= UMMA_PF_SLOTS * 128;
     const size_t smem = UmmaScoreSmem<KP>::total(a.red_bytes, a.var_bytes);
-    int grid = g.sm_count * umma_occupancy(KP, mode, smem);
+    int grid = g.sm_count * umma_occupancy(KP, mode, pf, smem);
     if (grid > a.num_tiles) grid = a.num_tiles;
     switch (mode) {
-        case LOAD_DENSE1: score_umma_kernel<KP, LOAD_DENSE1><<<grid, 128, smem, stream>>>(a); break;
-        case LOAD_DENSE2: score_umma_kernel<KP, LOAD_DENSE2><<<grid, 128, smem, stream>>>(a); break;
-        case LOAD_DENSE4: score_umma_kernel<KP, LOAD_DENSE4><<<grid, 128, smem, stream>>>(a); break;
-        case LOAD_GEN4: score_umma_kernel<KP, LOAD_GEN4><<<grid, 128, smem, stream>>>(a); break;
-        case LOAD_GEN2: score_umma_kernel<KP, LOAD_GEN2><<<grid, 128, smem, stream>>>(a); break;
-        default: score_umma_kernel<KP, LOAD_GEN1><<<grid, 128, smem, stream>>>(a); break;
+        case LOAD_DENSE1:
+            if (pf) score_umma_kernel<KP, LOAD_DENSE1, true><<<grid, 128, smem, stream>>>(a);
+            else score_umma_kernel<KP, LOAD_DENSE1, false><<<grid, 128, smem, stream>>>(a);
+            break;
+        case LOAD_DENSE2:
+            if (pf) score_umma_kernel<KP, LOAD_DENSE2, true><<<grid, 128, smem, stream>>>(a);
+            else score_umma_kernel<KP, LOAD_DENSE2, false><<<grid, 128, smem, stream>>>(a);
+            break;
+        case LOAD_DENSE4:
+            if (pf) score_umma_kernel<KP, LOAD_DENSE4, true><<<grid, 128, smem, stream>>>(a);
+            else score_umma_kernel<KP, LOAD_DENSE4, false><<<grid, 128, smem, stream>>>(a);
+            break;
+        case LOAD_GEN4: score_umma_kernel<KP, LOAD_GEN4, false><<<grid, 128, smem, stream>>>(a); break;
+        case LOAD_GEN2: score_umma_kernel<KP, LOAD_GEN2, false><<<grid, 128, smem, stream>>>(a); break;
+        default: score_umma_kernel<KP, LOAD_GEN1, false><<<grid, 128, smem, stream>>>(a); break;
     }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
@@ -337,8 +350,8 @@ int dctp_occupancy(int kp, int mode) {
     int rc = ensure_init();
     if (rc) return rc;
     if ((kp != 64 && kp != 128) || mode < 0 || mode > 5) return fail(DCTP_E_INVALID, "dctp_occupancy(%d, %d)", kp, mode);
-    const size_t smem = kp == 64 ? UmmaScoreSmem<64>::total(512, 3136) : UmmaScoreSmem<128>::total(512, 8192);
-    return umma_occupancy(kp, mode, smem);
+    const size_t smem = kp == 64 ? UmmaScoreSmem<64>::total(2048, 3136) : UmmaScoreSmem<128>::total(2560, 3200);
+    return umma_occupancy(kp, mode, mode <= LOAD_DENSE4, smem);
 }
 
 int dctp_prepare(int H, int W) {

@@ -29,9 +29,10 @@
 // would leak into live lanes.)
 //
 // Everything that is the same for every tile is computed once: the scatter table (where each loaded
-// vector lands in the swizzled operand: built on the host, staged into shared memory), the MMA
-// descriptor list, each lane's A2 store offsets.  Several CTAs share an SM (4 at KP = 64), so one
-// CTA's HBM round trip hides behind the others' tensor and epilogue phases.
+// vector lands in the swizzled operand: built on the host, staged into shared memory), the operand
+// descriptors, each lane's A2 store offsets.  Latency is hidden twice over: the loads of tile t+1 are
+// issued into registers right after tile t's stage-1 MMAs (they land while the tensor core and the
+// epilogues run), and several CTAs share an SM (4 at KP = 64).
 #pragma once
 #include "umma.cuh"
 
@@ -184,8 +185,6 @@ template <> struct Scatter<4> {
 
 }  // namespace detail
 
-constexpr uint32_t UMMA_MAX_MMAS = 48;      // 3 passes x (<= 8 k-steps) for each of the two stages
-
 template <int KP>
 struct UmmaScoreSmem {
     static_assert(KP == 64 || KP == 128, "contraction width");
@@ -197,8 +196,7 @@ struct UmmaScoreSmem {
     static constexpr uint32_t OFF_B_HI = OFF_A_LO + A_BYTES;
     static constexpr uint32_t OFF_B_LO = OFF_B_HI + B_BYTES;
     static constexpr uint32_t OFF_CTRL = OFF_B_LO + B_BYTES;       // mbarrier + TMEM slot
-    static constexpr uint32_t OFF_MMAS = OFF_CTRL + 64;            // precomputed MMA descriptor list
-    static constexpr uint32_t OFF_VAR = OFF_MMAS + UMMA_MAX_MMAS * 32;   // reduction scratch, then scatter table (dense) or map pointers (generic)
+    static constexpr uint32_t OFF_VAR = OFF_CTRL + 64;             // reduction scratch, then scatter table (dense) or map pointers (generic)
     static constexpr uint32_t FIXED = OFF_VAR;
     static constexpr uint32_t TMEM_COLS = 2 * KP;                  // D1 | D2
     __host__ __device__ static constexpr uint32_t total(uint32_t red_bytes, uint32_t var_bytes) {
@@ -206,14 +204,20 @@ struct UmmaScoreSmem {
     }
 };
 
-template <int KP, int MODE>
+constexpr int UMMA_PF_SLOTS = 13;          // prefetch registers: 13 float4 per thread = a 1568-vector tile (56^2, 28^2, 14^2, 7^2)
+
+// PF: keep the next tile's loads in flight (in registers) across this tile's tensor and epilogue phases.
+template <int KP, int MODE, bool PF>
 __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const UmmaScoreArgs a) {
     using S = UmmaScoreSmem<KP>;
     using namespace umma;
     constexpr bool DENSE = MODE <= LOAD_DENSE4;
+    static_assert(DENSE || !PF, "prefetch goes with the dense load path");
     constexpr int VPE = MODE == LOAD_DENSE1 ? 1 : MODE == LOAD_DENSE2 ? 2 : 4;
     constexpr int VEC = MODE == LOAD_GEN4 ? 4 : MODE == LOAD_GEN2 ? 2 : 1;
     constexpr int NCHUNK = KP / 8;                                 // 8-column chunks of a D1 row
+    constexpr int KSTEPS = KP / 16;                                // most k-steps a stage can have
+    constexpr int SLOTS = PF ? UMMA_PF_SLOTS : 1;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_hi = smem + S::OFF_A_HI;
     uint8_t* a_lo = smem + S::OFF_A_LO;
@@ -221,8 +225,7 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
     uint8_t* b_lo = smem + S::OFF_B_LO;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::OFF_CTRL);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_CTRL + 8);
-    uint4* mmas = reinterpret_cast<uint4*>(smem + S::OFF_MMAS);
-    float* red = reinterpret_cast<float*>(smem + S::OFF_VAR);     // epilogue-2 scratch, [J <= 8][128 lanes]
+    float* red = reinterpret_cast<float*>(smem + S::OFF_VAR);     // epilogue-2 scratch, [<= 8 rows][128 lanes]
     const float** mptr = reinterpret_cast<const float**>(smem + S::OFF_VAR + a.red_bytes);   // generic modes
     const typename detail::Scatter<VPE>::Entry* scat =
         reinterpret_cast<const typename detail::Scatter<VPE>::Entry*>(smem + S::OFF_VAR + a.red_bytes);  // dense modes
@@ -233,7 +236,25 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         return;
     }
 
-    // ---- one-time setup: zero the operand area, stage basis and scatter table, MMA list, TMEM, barrier
+    // ---- prefetch of the first tile goes out before anything else
+    [[maybe_unused]] float4 pf[SLOTS];
+    [[maybe_unused]] uint32_t pf_full = 0;
+    auto tile_vectors = [&](int tile) -> uint32_t {                // whole float4 vectors of this tile's stream
+        const long long left = a.total_elems - static_cast<long long>(tile) * a.MT * a.NN;
+        return static_cast<uint32_t>(min(static_cast<long long>(a.tile_vec), left >> 2));
+    };
+    auto prefetch = [&](int tile) {
+        pf_full = tile_vectors(tile);
+        const float4* src = reinterpret_cast<const float4*>(a.x_dense + static_cast<long long>(tile) * a.MT * a.NN) + tid;
+#pragma unroll
+        for (int u = 0; u < SLOTS; ++u)
+            if (tid + u * 128 < pf_full) pf[u] = detail::ldg_stream(src + u * 128);
+    };
+    if constexpr (PF) {
+        if ((int)blockIdx.x < a.num_tiles) prefetch(blockIdx.x);
+    }
+
+    // ---- one-time setup: zero the operand area, stage basis and scatter table, TMEM, barrier
     for (uint32_t off = tid * 16; off < S::OFF_B_HI; off += 128 * 16)
         *reinterpret_cast<uint4*>(smem + off) = make_uint4(0, 0, 0, 0);
     for (uint32_t i = tid; i < KP * (KP / 8); i += 128) {
@@ -249,30 +270,6 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         uint4* dst = reinterpret_cast<uint4*>(smem + S::OFF_VAR + a.red_bytes);
         for (uint32_t i = tid; i < (a.var_bytes + 15) / 16; i += 128) dst[i] = src[i];
     }
-    const uint32_t n_mma1 = 3u * a.K1, n_mma2 = 3u * a.NQ * a.K2S;
-    if (tid < n_mma1 + n_mma2) {
-        // entry = {A descriptor, B descriptor | TMEM column, accumulate flag, instruction descriptor}
-        uint64_t da, db;
-        uint32_t dcol, acc, idesc;
-        if (tid < n_mma1) {
-            const uint32_t pass = tid / a.K1, ks = tid - pass * a.K1;
-            const uint32_t a_off = (ks >> 2) * (128u * 128u) + (ks & 3) * 32u;
-            const uint32_t b_off = (ks >> 2) * (KP * 128u) + (ks & 3) * 32u;
-            da = make_smem_desc(smem_u32(pass == 1 ? a_lo : a_hi) + a_off, 16, 1024, SWIZZLE_128B);
-            db = make_smem_desc(smem_u32(pass == 2 ? b_lo : b_hi) + b_off, 16, 1024, SWIZZLE_128B);
-            dcol = 0; acc = tid != 0; idesc = a.idesc1;
-        } else {
-            const uint32_t i = tid - n_mma1, per_q = 3u * a.K2S;
-            const uint32_t q = i / per_q, r = i - q * per_q, pass = r / a.K2S, ks = r - pass * a.K2S;
-            const uint32_t b_off = (ks >> 2) * (KP * 128u) + (ks & 3) * 32u;
-            da = make_smem_desc(smem_u32(pass == 1 ? a_lo : a_hi) + q * a.a2_group_bytes + ks * 2048u, a.a2_lbo, 1024, SWIZZLE_128B);
-            db = make_smem_desc(smem_u32(pass == 2 ? b_lo : b_hi) + b_off, 16, 1024, SWIZZLE_128B);
-            dcol = KP + q * a.N2; acc = r != 0; idesc = a.idesc2;
-        }
-        mmas[2 * tid] = make_uint4(static_cast<uint32_t>(da), static_cast<uint32_t>(da >> 32), static_cast<uint32_t>(db),
-                                   static_cast<uint32_t>(db >> 32));
-        mmas[2 * tid + 1] = make_uint4(dcol, acc, idesc, 0);
-    }
     if (warp == 0) tmem_alloc<S::TMEM_COLS>(tmem_slot);
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -285,14 +282,64 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
     const uint32_t tmem = *tmem_slot;
     const uint32_t tmem_lane = tmem + ((warp * 32u) << 16);
 
+    // operand descriptors: high words are per layout, low words (start address) advance per k-step / group
+    // (the low word carries the start address in bits [0,14) and the leading-dimension offset in [16,30))
+    const uint64_t desc_k = make_smem_desc(0, 16, 1024, SWIZZLE_128B);            // K-major A1 and B
+    const uint64_t desc_mn = make_smem_desc(0, a.a2_lbo, 1024, SWIZZLE_128B);     // MN-major A2
+    const uint32_t k_lo = static_cast<uint32_t>(desc_k), mn_lo = static_cast<uint32_t>(desc_mn);
+    const uint32_t lo_a_hi = smem_u32(a_hi) >> 4, lo_a_lo = smem_u32(a_lo) >> 4;
+    const uint32_t lo_b_hi = smem_u32(b_hi) >> 4, lo_b_lo = smem_u32(b_lo) >> 4;
+
+    auto issue_stage1 = [&]() {                                    // one thread; D1 = A1 * B^T as hi*hi + lo*hi + hi*lo
+        tc_fence_after_sync();
+        uint32_t acc = 0;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t la = pass == 1 ? lo_a_lo : lo_a_hi, lb = pass == 2 ? lo_b_lo : lo_b_hi;
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                if (ks < a.K1) {
+                    mma_bf16_ss(tmem, desc_with_lo(desc_k, k_lo + la + (ks >> 2) * 1024 + (ks & 3) * 2),
+                                desc_with_lo(desc_k, k_lo + lb + (ks >> 2) * (KP * 8) + (ks & 3) * 2), a.idesc1, acc);
+                    acc = 1;
+                }
+            }
+        }
+        mma_commit(bar);
+    };
+    auto issue_stage2 = [&]() {                                    // per column group: D2 = A2_q * C^T
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (uint32_t q = 0; q < (uint32_t)a.NQ; ++q) {
+            const uint32_t qoff = q * (a.a2_group_bytes >> 4), dcol = tmem + KP + q * a.N2;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t la = (pass == 1 ? lo_a_lo : lo_a_hi) + qoff, lb = pass == 2 ? lo_b_lo : lo_b_hi;
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    if (ks < a.K2S) {
+                        mma_bf16_ss(dcol, desc_with_lo(desc_mn, mn_lo + la + ks * 128),
+                                    desc_with_lo(desc_k, k_lo + lb + (ks >> 2) * (KP * 8) + (ks & 3) * 2), a.idesc2, acc);
+                        acc = 1;
+                    }
+                }
+            }
+        }
+        mma_commit(bar);
+    };
+
     // this thread's TMEM lane as (lane group, row in map), and where its D1 chunks go in A2
     const uint32_t my_g = a.div_ms.div(tid);
     const uint32_t my_r = tid - my_g * a.Ms;
     const bool lane_in_map = my_g < (uint32_t)a.G && my_r < (uint32_t)a.N;
     const uint32_t used_cols = a.J * a.Ms;
     const bool ms8 = a.Ms == 8;
-    const uint32_t col_lim = ms8 ? 16u : (uint32_t)a.Ms;   // meaningful D2 columns per stage-2 group
-    const uint32_t blocks_per_q = a.N2 >> 4;               // x16 column blocks per stage-2 group
+    const uint32_t col_lim = ms8 ? 16u : (uint32_t)a.Ms;           // meaningful D2 columns per stage-2 group
+    const uint32_t blocks_per_q = a.N2 >> 4;                       // x16 column blocks per stage-2 group
+    const uint32_t n_blocks = a.NQ * blocks_per_q;                 // x16 column blocks holding coefficients
+    // D2 columns in [Ms, N2) are exact zeros unless a neighbouring map's basis block reaches into them
+    const bool mask_cols = !ms8 && a.J > 1 && (a.Ms & 15) != 0;
     uint32_t a2off[NCHUNK];
 #pragma unroll
     for (int ci = 0; ci < NCHUNK; ++ci) {
@@ -305,16 +352,6 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
     uint32_t phase = 0;
     bool alive = true;
 
-    auto issue = [&](uint32_t first, uint32_t count) {             // one thread: the precomputed MMA list
-        tc_fence_after_sync();
-#pragma unroll 1
-        for (uint32_t i = first; i < first + count; ++i) {
-            const uint4 d = mmas[2 * i], m = mmas[2 * i + 1];
-            mma_bf16_ss(tmem + m.x, (static_cast<uint64_t>(d.y) << 32) | d.x, (static_cast<uint64_t>(d.w) << 32) | d.z, m.z, m.y);
-        }
-        mma_commit(bar);
-    };
-
     for (int tile = blockIdx.x; tile < a.num_tiles && alive; tile += gridDim.x) {
         const int map0 = tile * a.MT;
         const int maps_here = min(a.MT, a.n_maps - map0);
@@ -322,21 +359,29 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         // ---- stage 0: HBM -> registers -> bf16 hi/lo -> A1 (each scored map is read exactly once)
         if constexpr (DENSE) {
             const long long elem0 = static_cast<long long>(map0) * a.NN;
-            const long long left = a.total_elems - elem0;
-            const uint32_t n_full = static_cast<uint32_t>(min(static_cast<long long>(a.tile_vec), left >> 2));
-            const float4* src = reinterpret_cast<const float4*>(a.x_dense + elem0);
-            constexpr int U = 8;                                   // 8 x 16 B in flight per thread; x 4 CTAs covers the HBM latency
+            uint32_t n_full;
+            if constexpr (PF) {
+                n_full = pf_full;
+#pragma unroll
+                for (int u = 0; u < SLOTS; ++u)
+                    if (tid + u * 128 < n_full) detail::Scatter<VPE>::st(a_hi, a_lo, scat[tid + u * 128], pf[u]);
+            } else {
+                n_full = tile_vectors(tile);
+                const float4* src = reinterpret_cast<const float4*>(a.x_dense + elem0);
+                constexpr int U = 8;                               // 8 x 16 B in flight per thread; x 4 CTAs covers the HBM latency
 #pragma unroll 1
-            for (uint32_t base = tid; base < n_full; base += 128 * U) {
-                float4 v[U];
+                for (uint32_t base = tid; base < n_full; base += 128 * U) {
+                    float4 v[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (base + u * 128 < n_full) v[u] = detail::ldg_stream(src + base + u * 128);
+                    for (int u = 0; u < U; ++u)
+                        if (base + u * 128 < n_full) v[u] = detail::ldg_stream(src + base + u * 128);
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (base + u * 128 < n_full) detail::Scatter<VPE>::st(a_hi, a_lo, scat[base + u * 128], v[u]);
+                    for (int u = 0; u < U; ++u)
+                        if (base + u * 128 < n_full) detail::Scatter<VPE>::st(a_hi, a_lo, scat[base + u * 128], v[u]);
+                }
             }
             if constexpr (VPE == 4) {                              // odd sizes: the stream may end inside a float4
+                const long long left = a.total_elems - elem0;
                 const uint32_t tail = static_cast<uint32_t>(min(static_cast<long long>(a.tile_vec) * 4, left)) - n_full * 4;
                 if (tid < tail && n_full < (uint32_t)a.tile_vec) {
                     const float x = a.x_dense[elem0 + n_full * 4 + tid];
@@ -384,8 +429,12 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         fence_async_smem();
         __syncthreads();
 
-        // ---- stage 1 MMA: D1 = A1 * B^T  (hi*hi + lo*hi + hi*lo)
-        if (tid == 0) issue(0, n_mma1);
+        // ---- stage 1 MMA; the next tile's loads go out while the tensor core and the epilogues work
+        if (tid == 0) issue_stage1();
+        if constexpr (PF) {
+            const int next = tile + (int)gridDim.x;
+            if (next < a.num_tiles) prefetch(next);
+        }
         if (!mbar_wait(bar, phase)) alive = false;
         phase ^= 1;
         tc_fence_after_sync();
@@ -420,16 +469,15 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         __syncthreads();
 
         // ---- stage 2 MMA: per column group, D2 = A2_q * C^T, contraction over the map's rows
-        if (tid == 0) issue(n_mma1, n_mma2);
+        if (tid == 0) issue_stage2();
         if (!mbar_wait(bar, phase)) alive = false;
         phase ^= 1;
         tc_fence_after_sync();
 
-        // ---- epilogue 2: coefficients -> energy, never leaving the SM.  Lane = (g, v); column = (q, n).
+        // ---- epilogue 2: coefficients -> energy, never leaving the SM.  Lane = (g, v); x16 block = (q, 16 columns).
+        //      red[row][lane]: one row per block (two per block when Ms == 8: the block holds two maps)
         {
-            const uint32_t n_blocks = a.NQ * blocks_per_q;         // x16 column blocks holding coefficients
-            float e_acc = 0.f;
-            uint32_t q = 0, in_q = 0;
+            uint32_t q = 0, in_q = 0;                              // group of the current block, block index inside it
 #pragma unroll
             for (int part = 0; part < KP / 32; ++part) {
                 if ((uint32_t)(part * 2) < n_blocks) {
@@ -440,48 +488,46 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
                         if ((uint32_t)(part * 2 + b) < n_blocks) {
-                            const uint32_t c0 = in_q * 16;         // first column of this block inside its group
                             float e0 = 0.f, e1 = 0.f;
-                            if (c0 + 16 <= col_lim) {
+                            if (mask_cols) {                       // leftovers past the group's own map: masked
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    float z0 = in_q * 16 + i < col_lim ? __uint_as_float(r[b][i]) : 0.f;
+                                    float z1 = in_q * 16 + 8 + i < col_lim ? __uint_as_float(r[b][8 + i]) : 0.f;
+                                    e0 = fmaf(z0, z0, e0);
+                                    e1 = fmaf(z1, z1, e1);
+                                }
+                            } else {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     float z0 = __uint_as_float(r[b][i]), z1 = __uint_as_float(r[b][8 + i]);
                                     e0 = fmaf(z0, z0, e0);
                                     e1 = fmaf(z1, z1, e1);
                                 }
-                            } else {                               // columns past the group's own map hold leftovers: masked
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    float z0 = c0 + i < col_lim ? __uint_as_float(r[b][i]) : 0.f;
-                                    float z1 = c0 + 8 + i < col_lim ? __uint_as_float(r[b][8 + i]) : 0.f;
-                                    e0 = fmaf(z0, z0, e0);
-                                    e1 = fmaf(z1, z1, e1);
-                                }
-                            }
-                            if (a.dump != nullptr && lane_in_map) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    uint32_t n = c0 + i;
-                                    uint32_t j = ms8 ? (2 * q + (n >> 3)) : q;
-                                    uint32_t u = ms8 ? (n & 7) : n;
-                                    int t = (int)(my_g * a.J + j);
-                                    if (u < (uint32_t)a.N && j < (uint32_t)a.J && t < maps_here)
-                                        a.dump[(long long)(map0 + t) * a.NN + u * a.N + my_r] = __uint_as_float(r[b][i]);
-                                }
                             }
                             if (ms8) {
-                                red[(2 * q) * 128 + tid] = e0;
-                                red[(2 * q + 1) * 128 + tid] = e1;
-                                ++q;
+                                red[(2 * (part * 2 + b)) * 128 + tid] = e0;
+                                red[(2 * (part * 2 + b) + 1) * 128 + tid] = e1;
                             } else {
-                                e_acc += e0 + e1;
-                                if (++in_q == blocks_per_q) {
-                                    red[q * 128 + tid] = e_acc;
-                                    e_acc = 0.f;
-                                    in_q = 0;
-                                    ++q;
+                                red[(part * 2 + b) * 128 + tid] = e0 + e1;
+                            }
+                            if (a.dump != nullptr) {
+                                if (lane_in_map) {
+#pragma unroll 1
+                                    for (int i = 0; i < 16; ++i) {
+                                        uint32_t n = in_q * 16 + i;
+                                        uint32_t j = ms8 ? (2 * q + (n >> 3)) : q;
+                                        uint32_t u = ms8 ? (n & 7) : n;
+                                        int t = (int)(my_g * a.J + j);
+                                        float z = 0.f;
+#pragma unroll
+                                        for (int s = 0; s < 16; ++s) z = s == i ? __uint_as_float(r[b][s]) : z;
+                                        if (u < (uint32_t)a.N && j < (uint32_t)a.J && t < maps_here)
+                                            a.dump[(long long)(map0 + t) * a.NN + u * a.N + my_r] = z;
+                                    }
                                 }
                             }
+                            if (++in_q == blocks_per_q) { in_q = 0; ++q; }
                         }
                     }
                 }
@@ -495,9 +541,12 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
             float s = 0.f;
             const bool live = (int)t < maps_here;
             if (live) {
-                uint32_t g = a.div_j.div(t), j = t - g * a.J;
-                const float* rp = red + j * 128 + g * a.Ms;
-                for (uint32_t v = sub; v < (uint32_t)a.N; v += a.TPM) s += rp[v];
+                const uint32_t g = a.div_j.div(t), j = t - g * a.J;
+                const uint32_t rows = ms8 ? 1u : blocks_per_q, first = ms8 ? j : j * blocks_per_q;
+                for (uint32_t row = 0; row < rows; ++row) {
+                    const float* rp = red + (first + row) * 128 + g * a.Ms;
+                    for (uint32_t v = sub; v < (uint32_t)a.N; v += a.TPM) s += rp[v];
+                }
             }
             for (uint32_t o = a.TPM >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (live && sub == 0) {

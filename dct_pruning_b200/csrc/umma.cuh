@@ -24,16 +24,18 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_init_fence() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// One probe; the thread is suspended in hardware (no issue slots burnt) until the phase completes or
+// `suspend_ns` has passed, whichever is first.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t suspend_ns = 20000u) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(suspend_ns)
         : "memory");
     return ok != 0;
 }
@@ -51,7 +53,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
     for (;;) {
 #pragma unroll 1
-        for (int spin = 0; spin < 64; ++spin)
+        for (int spin = 0; spin < 16; ++spin)
             if (mbar_try_wait(bar, parity)) return true;
         if (global_ns() - t0 > 2000000000ull) return false;
     }
@@ -125,6 +127,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // advance the 14-bit start-address field by `bytes` (stays inside the same swizzle atom row / next atom)
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) {
     return desc + static_cast<uint64_t>(bytes >> 4);
+}
+
+// the 14-bit start-address field sits in the low word: advancing by `bytes` never carries out of it here
+__device__ __forceinline__ uint64_t desc_with_lo(uint64_t desc, uint32_t lo) {
+    return (desc & 0xFFFFFFFF00000000ull) | lo;
 }
 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {
