@@ -352,11 +352,13 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
     uint32_t phase = 0;
     bool alive = true;
 
-    for (int tile = blockIdx.x; tile < a.num_tiles && alive; tile += gridDim.x) {
+    // ---- phases of one tile.  Software pipeline across tiles (one mbarrier, strictly alternating phases):
+    //        stage0(t+1) and MMA1(t+1) are issued as soon as MMA2(t) has released the operand buffer, so
+    //        epilogue 2 and the reduction of tile t run while the tensor core already works on tile t+1.
+    auto stage0 = [&](int tile) {
         const int map0 = tile * a.MT;
-        const int maps_here = min(a.MT, a.n_maps - map0);
-
-        // ---- stage 0: HBM -> registers -> bf16 hi/lo -> A1 (each scored map is read exactly once)
+        [[maybe_unused]] const int maps_here = min(a.MT, a.n_maps - map0);
+        // HBM -> registers -> bf16 hi/lo -> A1 (each scored map is read exactly once)
         if constexpr (DENSE) {
             const long long elem0 = static_cast<long long>(map0) * a.NN;
             uint32_t n_full;
@@ -428,18 +430,14 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         }
         fence_async_smem();
         __syncthreads();
-
-        // ---- stage 1 MMA; the next tile's loads go out while the tensor core and the epilogues work
         if (tid == 0) issue_stage1();
-        if constexpr (PF) {
-            const int next = tile + (int)gridDim.x;
+        if constexpr (PF) {                                        // the following tile's loads go out now and land
+            const int next = tile + (int)gridDim.x;                // while the tensor core and the epilogues work
             if (next < a.num_tiles) prefetch(next);
         }
-        if (!mbar_wait(bar, phase)) alive = false;
-        phase ^= 1;
-        tc_fence_after_sync();
-
-        // ---- epilogue 1: D1 row (g,h) -> bf16 hi/lo -> A2_q[(g, v), k]   (MN-major operand, aliases A1)
+    };
+    auto epilogue1 = [&]() {
+        // D1 row (g,h) -> bf16 hi/lo -> A2_q[(g, v), k]   (MN-major operand, aliases A1)
 #pragma unroll
         for (int part = 0; part < KP / 32; ++part) {               // 32 columns at a time keeps the register footprint small
             if ((uint32_t)(part * 32) < (uint32_t)a.N1) {
@@ -467,14 +465,12 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         tc_fence_before_sync();
         fence_async_smem();
         __syncthreads();
-
-        // ---- stage 2 MMA: per column group, D2 = A2_q * C^T, contraction over the map's rows
         if (tid == 0) issue_stage2();
-        if (!mbar_wait(bar, phase)) alive = false;
-        phase ^= 1;
-        tc_fence_after_sync();
-
-        // ---- epilogue 2: coefficients -> energy, never leaving the SM.  Lane = (g, v); x16 block = (q, 16 columns).
+    };
+    auto epilogue2 = [&](int tile) {
+        const int map0 = tile * a.MT;
+        const int maps_here = min(a.MT, a.n_maps - map0);
+        // coefficients -> energy, never leaving the SM.  Lane = (g, v); x16 block = (q, 16 columns).
         //      red[row][lane]: one row per block (two per block when Ms == 8: the block holds two maps)
         {
             uint32_t q = 0, in_q = 0;                              // group of the current block, block index inside it
@@ -556,7 +552,22 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
                 if (a.energy_out) a.energy_out[mm] = s;
             }
         }
-        __syncthreads();          // `red` is rewritten by the next tile's epilogue
+    };
+
+    int tile = blockIdx.x;
+    if (tile < a.num_tiles) stage0(tile);
+    while (tile < a.num_tiles) {
+        const int next = tile + (int)gridDim.x;
+        if (!mbar_wait(bar, phase)) { alive = false; break; }      // MMA1(tile)
+        phase ^= 1;
+        tc_fence_after_sync();
+        epilogue1();
+        if (!mbar_wait(bar, phase)) { alive = false; break; }      // MMA2(tile): operand buffer and D1 are free again
+        phase ^= 1;
+        tc_fence_after_sync();
+        if (next < a.num_tiles) stage0(next);
+        epilogue2(tile);                                           // overlaps MMA1(next)
+        tile = next;
     }
 
     if (!alive && tid == 0) atomicExch(a.status, DCTP_DEV_MMA_TIMEOUT);

@@ -35,14 +35,16 @@ def generate(tag, device, path='auto'):
     return want, got
 
 
-FORWARD_NOISE_TOL = 2e-3     # cuDNN vs the reference's CPU convolutions on weak channels, NOT the scoring kernels (see the strict test below)
+FORWARD_EPS = 3e-5     # relative amplitude noise of a cuDNN fp32 forward vs the reference's CPU forward (not the scoring kernels)
 
 
 @pytest.mark.parametrize('tag', CASES)
 def test_scores_match_reference_end_to_end(lib, cuda_device, tag):
-    """Whole pipeline on the GPU (cuDNN forward included) vs the files the reference wrote.  The forward
-    passes differ in summation order, which moves weak channels by a few 1e-4 relative; strong channels
-    (>= 1% of the layer's largest score) still meet the 1e-4 bar."""
+    """Whole pipeline on the GPU (cuDNN forward included) vs the files the reference wrote.  The two forward
+    passes differ in summation order: activations move by ~FORWARD_EPS of the layer's typical amplitude, so a
+    channel of energy w in a layer whose strongest channel has energy S may move by 2*eps*sqrt(w*S).  Strong
+    channels (>= 1% of S) must still meet the 1e-4 bar outright.  The strict test below removes the forward
+    from the comparison."""
     want, got = generate(tag, cuda_device)
     assert sorted(want) == sorted(got)
     flipped = total = 0
@@ -50,12 +52,12 @@ def test_scores_match_reference_end_to_end(lib, cuda_device, tag):
         w, g = want[stem].astype(np.float64), got[stem].astype(np.float64)
         assert g.shape == w.shape and got[stem].dtype == np.float32
         scale = max(w.max(), 1e-30)
-        live = w > 1e-6 * scale
-        rel = np.abs(g - w) / np.maximum(w, 1e-30)
-        assert rel[live].max(initial=0) < FORWARD_NOISE_TOL, (stem, rel[live].max())
+        tol = 2 * FORWARD_EPS * np.sqrt(w * scale) + FORWARD_EPS ** 2 * scale + 1e-4 * w
+        bad = np.abs(g - w) > tol
+        assert not bad.any(), (stem, np.nonzero(bad)[0][:5], (np.abs(g - w) / np.maximum(w, 1e-30))[bad][:5])
         strong = w >= 1e-2 * scale
+        rel = np.abs(g - w) / np.maximum(w, 1e-30)
         assert rel[strong].max(initial=0) < 1e-4, (stem, rel[strong].max())
-        assert np.abs(g[~live] - w[~live]).max(initial=0) < 1e-6 * scale + 1e-12, stem
         flipped += int(((w == 0) != (g == 0)).sum())
         total += w.size
     assert flipped <= max(1, total // 200), 'cuDNN vs CPU forward flipped %d of %d dead channels' % (flipped, total)
