@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -11,6 +12,7 @@
 
 #include "../../include/dctp.h"
 #include "score_simt.cuh"
+#include "score_tmem.cuh"
 #include "score_umma.cuh"
 #include "topk.cuh"
 
@@ -39,6 +41,12 @@ struct UmmaBasis {                                                       // per 
     uint16_t* scatter = nullptr;                                         // [tile_vec][vpe] operand offsets of a dense tile (or null)
     int vpe = 0, tile_vec = 0;
 };
+struct TBasis {                                                          // per N: operands of the TMEM-operand kernel
+    uint32_t *a_hi = nullptr, *a_lo = nullptr;                           // [128][64] packed bf16 pairs of I_G (x) C_N
+    uint16_t *c_hi = nullptr, *c_lo = nullptr;                           // [64][64] C_N zero padded
+    uint16_t* scatter = nullptr;                                         // [tile_vec]
+    int tile_vec = 0;
+};
 struct SimtBasis { float* t = nullptr; };                               // [N x N], t[n*N + k] = C_N[k][n]
 
 struct State {
@@ -49,6 +57,9 @@ struct State {
     long long launches = 0;
     std::map<std::pair<int, int>, UmmaBasis> umma;     // (N, KP)
     std::map<int, SimtBasis> simt;                     // N
+    std::map<int, TBasis> tmem;                        // N
+    int t_slots = 3;                                   // tile slots per CTA of the TMEM-operand kernel (DCTP_T_SLOTS=0 disables it)
+    int t_wps = 8;                                     // warps per tile slot (DCTP_T_WPS=4|8)
     int regs[2][6][2] = {};                            // registers/thread per (KP, load mode, prefetch) instantiation
     // scratch of dctp_score_host (grow-only)
     float* hx = nullptr; size_t hx_bytes = 0;
@@ -109,6 +120,45 @@ int get_umma_basis(int N, int KP, UmmaBasis& out) {
         CUDA_TRY(cudaMemcpy(b.scatter, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice));
     }
     g.umma[key] = b;
+    out = b;
+    return DCTP_OK;
+}
+
+int get_t_basis(int N, TBasis& out) {
+    auto it = g.tmem.find(N);
+    if (it != g.tmem.end()) { out = it->second; return DCTP_OK; }
+    const int Ms = (N + 7) / 8 * 8, G = 128 / Ms, NN = N * N;
+    std::vector<uint32_t> ahi(128 * 64, 0), alo(128 * 64, 0);
+    std::vector<uint16_t> chi(64 * 64, 0), clo(64 * 64, 0);
+    for (int gI = 0; gI < G; ++gI)
+        for (int v = 0; v < N; ++v)
+            for (int w = 0; w < N; ++w) {
+                uint16_t h, l;
+                split_bf16(dct_coef(v, w, N), h, l);
+                const int row = gI * Ms + v, k = gI * N + w;          // element k of the row sits in half (k & 1) of packed column k / 2
+                ahi[row * 64 + k / 2] |= static_cast<uint32_t>(h) << (16 * (k & 1));
+                alo[row * 64 + k / 2] |= static_cast<uint32_t>(l) << (16 * (k & 1));
+            }
+    for (int u = 0; u < N; ++u)
+        for (int h = 0; h < N; ++h) split_bf16(dct_coef(u, h, N), chi[u * 64 + h], clo[u * 64 + h]);
+    TBasis b;
+    b.tile_vec = G * NN / 4;
+    std::vector<uint16_t> tab(static_cast<size_t>(b.tile_vec) + 8, 0);
+    for (int v = 0; v < b.tile_vec; ++v) {
+        const int e = 4 * v, gI = e / NN, r = e % NN;
+        tab[v] = static_cast<uint16_t>(detail::kmajor_off(r / N, gI * N + r % N, 64));
+    }
+    CUDA_TRY(cudaMalloc(&b.a_hi, ahi.size() * 4));
+    CUDA_TRY(cudaMalloc(&b.a_lo, alo.size() * 4));
+    CUDA_TRY(cudaMalloc(&b.c_hi, chi.size() * 2));
+    CUDA_TRY(cudaMalloc(&b.c_lo, clo.size() * 2));
+    CUDA_TRY(cudaMalloc(&b.scatter, tab.size() * 2));
+    CUDA_TRY(cudaMemcpy(b.a_hi, ahi.data(), ahi.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.a_lo, alo.data(), alo.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.c_hi, chi.data(), chi.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.c_lo, clo.data(), clo.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.scatter, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice));
+    g.tmem[N] = b;
     out = b;
     return DCTP_OK;
 }
@@ -182,6 +232,17 @@ int ensure_init() {
     int rc;
     if ((rc = setup_umma_all<64>(g.regs[0]))) return rc;
     if ((rc = setup_umma_all<128>(g.regs[1]))) return rc;
+    {
+        const void* fns[] = {reinterpret_cast<const void*>(score_t_kernel<1, 4>), reinterpret_cast<const void*>(score_t_kernel<3, 4>),
+                             reinterpret_cast<const void*>(score_t_kernel<2, 8>), reinterpret_cast<const void*>(score_t_kernel<3, 8>)};
+        for (const void* fn : fns) {
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+    }
+    if (const char* e = std::getenv("DCTP_T_WPS")) g.t_wps = std::atoi(e) == 4 ? 4 : 8;
+    if (const char* e = std::getenv("DCTP_T_SLOTS")) g.t_slots = std::atoi(e);
+    if (g.t_slots < 0 || g.t_slots > 3) g.t_slots = 3;
     CUDA_TRY(cudaFuncSetAttribute(score_simt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMALL_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(score_simt_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CUDA_TRY(cudaMalloc(&g.status, sizeof(int)));
@@ -206,6 +267,68 @@ int pick_vec(const float* x, long long stride_b, long long stride_c, int c_begin
     if (aligned(4)) return 4;
     if (aligned(2)) return 2;
     return 1;
+}
+
+// TMEM-operand kernel: dense tensors, N % 4 == 0, 16 <= N <= 64
+bool t_shape_ok(int N) { return g.t_slots > 0 && N >= 16 && N <= 64 && (N % 4) == 0; }
+
+int launch_t(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
+    TBasis basis;
+    int rc = get_t_basis(N, basis);
+    if (rc) return rc;
+    TScoreArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.x_dense = first; a.n_maps = B * c_count; a.c_count = c_count;
+    a.N = N; a.NN = N * N; a.Ms = (N + 7) / 8 * 8; a.G = 128 / a.Ms;
+    a.total_elems = static_cast<long long>(a.n_maps) * a.NN;
+    a.tile_vec = basis.tile_vec;
+    a.num_tiles = (a.n_maps + a.G - 1) / a.G;
+    a.K1S = (a.G * N + 15) / 16; a.N1 = (N + 15) / 16 * 16;
+    a.TPM = pow2_floor(128 / a.G < 32 ? 128 / a.G : 32);
+    a.idesc = umma::make_idesc_bf16(128, a.N1, false, false);
+    a.scatter = basis.scatter; a.scatter_bytes = static_cast<uint32_t>(basis.tile_vec) * 2u;
+    a.a_hi = basis.a_hi; a.a_lo = basis.a_lo; a.c_hi = basis.c_hi; a.c_lo = basis.c_lo;
+    a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
+    if (const char* e = std::getenv("DCTP_T_DUMP_STAGE")) a.dump_stage = std::atoi(e);
+    static long long* trace_buf = nullptr;
+    const bool tracing = std::getenv("DCTP_T_TRACE") != nullptr;
+    if (tracing) {
+        if (!trace_buf) CUDA_TRY(cudaMalloc(&trace_buf, 256 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(trace_buf, 0, 256 * sizeof(long long)));
+        a.trace = trace_buf;
+    }
+    a.div_ms.set(a.Ms);
+    int ns = g.t_slots, wps = g.t_wps;
+    if (wps == 4 && ns == 2) ns = 3;                   // instantiated: (1,4) (3,4) (2,8) (3,8)
+    if (wps == 8 && ns == 1) ns = 2;
+    const size_t smem = TScoreSmem::total(ns, a.scatter_bytes);
+    const int ctas_per_sm = (ns == 1 && wps == 4) ? 2 : 1;
+    int grid = g.sm_count * ctas_per_sm;
+    const int need = (a.num_tiles + ns - 1) / ns;
+    if (grid > need) grid = need;
+    if (wps == 4 && ns == 1) score_t_kernel<1, 4><<<grid, 128, smem, stream>>>(a);
+    else if (wps == 4) score_t_kernel<3, 4><<<grid, 384, smem, stream>>>(a);
+    else if (ns == 2) score_t_kernel<2, 8><<<grid, 512, smem, stream>>>(a);
+    else score_t_kernel<3, 8><<<grid, 768, smem, stream>>>(a);
+    if (tracing) {
+        long long h[256];
+        CUDA_TRY(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
+        const char* names[7] = {"convert", "fence+bar", "issue1+prefetch", "wait1", "epi1+bar", "issue2+wait2", "epi2+reduce"};
+        double sum[7] = {0}; int n = 0; double gap = 0;
+        for (int t = 2; t < 32 && h[t * 8 + 7]; ++t, ++n) {
+            for (int k = 0; k < 7; ++k) sum[k] += double(h[t * 8 + k + 1] - h[t * 8 + k]);
+            gap += double(h[t * 8] - h[(t - 1) * 8 + 7]);
+        }
+        if (n) {
+            fprintf(stderr, "[dctp trace] N=%d tiles=%d cycles/tile:", N, n);
+            double tot = 0;
+            for (int k = 0; k < 7; ++k) { fprintf(stderr, " %s %.0f", names[k], sum[k] / n); tot += sum[k] / n; }
+            fprintf(stderr, " loop-gap %.0f total %.0f\n", gap / n, tot + gap / n);
+        }
+    }
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    return DCTP_OK;
 }
 
 template <int KP>
@@ -235,6 +358,8 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
     const float* first = x + static_cast<long long>(c_begin) * stride_c;
     const bool dense = basis.scatter != nullptr && stride_c == a.NN && (B == 1 || stride_b == static_cast<long long>(c_count) * a.NN) &&
                        (reinterpret_cast<uintptr_t>(first) % 16) == 0;
+    if (KP == 64 && dense && t_shape_ok(N))
+        return launch_t(first, B, N, c_count, accum, energy_out, coeff_out, stream);
     int mode;
     if (dense) {
         mode = basis.vpe == 1 ? LOAD_DENSE1 : basis.vpe == 2 ? LOAD_DENSE2 : LOAD_DENSE4;
@@ -330,7 +455,10 @@ int dctp_shutdown(void) {
     if (!g.ready) return DCTP_OK;
     for (auto& kv : g.umma) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); cudaFree(kv.second.scatter); }
     for (auto& kv : g.simt) cudaFree(kv.second.t);
-    g.umma.clear(); g.simt.clear();
+    for (auto& kv : g.tmem) {
+        cudaFree(kv.second.a_hi); cudaFree(kv.second.a_lo); cudaFree(kv.second.c_hi); cudaFree(kv.second.c_lo); cudaFree(kv.second.scatter);
+    }
+    g.umma.clear(); g.simt.clear(); g.tmem.clear();
     cudaFree(g.status); cudaFree(g.hx); cudaFree(g.hacc); cudaFree(g.hout);
     g = State();
     return DCTP_OK;
@@ -360,6 +488,11 @@ int dctp_prepare(int H, int W) {
     if (rc) return rc;
     if (H < 1 || W < 1) return fail(DCTP_E_INVALID, "dctp_prepare: H=%d W=%d", H, W);
     if (umma_shape_ok(H, W, W)) {
+        if (t_shape_ok(H)) {
+            TBasis tb;
+            int rc2 = get_t_basis(H, tb);
+            if (rc2) return rc2;
+        }
         UmmaBasis b;
         return get_umma_basis(H, H <= 64 ? 64 : 128, b);
     }

@@ -1,0 +1,347 @@
+// Fused DCT-score hook kernel, TMEM-operand formulation (maps of side 16..64, N % 4 == 0, dense tensors).
+//
+// Same contract as score_umma.cuh (/root/reference/utils/common.py:262-277: per-(image,channel)
+// orthonormal 2-D DCT-II energy, summed per channel), re-arranged because ncu shows the K-major/MN-major
+// formulation bound by SHARED-MEMORY bandwidth (tensor-core operand reads + thread stores = 85 % of the
+// L1/shared data pipe at 2.7 TB/s).  Here the only shared-memory operand traffic is the raw data once
+// and the small resident basis:
+//
+//   tile      G = 128 / Ms maps (Ms = N rounded up to 8), map g owns TMEM lanes [g*Ms, g*Ms + N)
+//   stage 1   D1[(g,v), h] = sum_{(g',w)} A'[(g,v),(g',w)] * Bx[h,(g',w)]
+//             A' = I_G (x) C_N  (block diagonal, bf16 hi/lo) lives in TMEM for the whole kernel  -> no smem reads
+//             Bx[h, g*N + w] = X_g[h, w]  is the data, K-major in shared memory, N-side operand (N1 rows)
+//             -> D1 = (C X^T) per map: the intermediate comes out TRANSPOSED, lanes (g,v), columns h
+//   epi   1   tcgen05.ld D1 -> bf16 hi/lo -> tcgen05.st A2 (packed pairs): stays in TMEM, no smem round trip
+//   stage 2   D2[(g,v), u] = sum_h A2[(g,v),h] * C[u,h]      A from TMEM, B = C_N resident in shared memory
+//   epi   2   tcgen05.ld D2 -> sum of squares per lane -> fixed-order tree over the map's lanes -> fp64 atomicAdd
+//
+// Three bf16 MMAs per product (hi*hi + hi*lo + lo*hi, fp32 accumulate).  Shared-memory wavefronts per 25 KB
+// of input: ~300 data stores + 336 + 192 basis/data operand reads, against ~2070 for the smem-operand kernel.
+// The price: the block-diagonal A' wastes a factor G of stage-1 tensor work (1056 tensor cycles per 25 KB at
+// 56x56 vs 768), still below the HBM time (1080 cycles at the measured 6.55 TB/s).
+//
+// TMEM: [0,128) A' (hi | lo, written once), then per tile slot 128 columns: D (64, D2 re-uses D1) | A2 hi (32) | A2 lo (32).
+// One CTA runs NSLOT independent tile slots, one warpgroup (4 warps = 128 TMEM lanes) each, sharing A' and C.
+#pragma once
+#include "score_umma.cuh"
+
+namespace dctp {
+
+namespace detail {
+// three passes x KS k-steps of D (+)= A[tmem] * B[smem]^T, fully unrolled.  Pass p reads the TMEM operand at
+// column a_p + 8*ks and the K-major shared-memory operand whose descriptor low word is b_p (+ k-step offset).
+template <int KS>
+__device__ __forceinline__ void issue_ts3(uint32_t d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b0, uint32_t b1, uint32_t b2,
+                                          uint64_t desc, uint32_t idesc) {
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t ac = pass == 0 ? a0 : pass == 1 ? a1 : a2;
+        const uint32_t bl = pass == 0 ? b0 : pass == 1 ? b1 : b2;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+            umma::mma_bf16_ts(d, ac + 8 * ks, umma::desc_with_lo(desc, bl + (ks >> 2) * 512 + (ks & 3) * 2), idesc,
+                              (pass | ks) != 0);
+    }
+}
+}  // namespace detail
+
+struct TScoreArgs {
+    const float* x_dense;           // first scored element; all scored maps back to back, 16-B aligned
+    long long total_elems;          // n_maps * NN
+    int n_maps, c_count;
+    int N, NN, Ms, G;
+    int tile_vec;                   // float4 vectors per full tile = G*NN/4
+    int num_tiles;
+    int K1S;                        // stage-1 k-steps = ceil(G*N / 16)
+    int N1;                         // N rounded up to 16: MMA N of both stages, contraction length of stage 2
+    int TPM;                        // threads per map in the final reduction
+    uint32_t idesc;                 // M = 128, N = N1, bf16 x bf16 -> f32, K-major B
+    const uint16_t* scatter;        // [tile_vec] byte offset of each float4 (as 4 bf16) in the K-major data operand
+    uint32_t scatter_bytes;
+    const uint32_t* a_hi;           // [128][64] packed bf16 pairs of A' = I_G (x) C_N (row (g,v), column pair (g',w)/2)
+    const uint32_t* a_lo;
+    const uint16_t* c_hi;           // [64][64] bf16 C_N zero padded (row u, column h)
+    const uint16_t* c_lo;
+    double* accum;
+    float* energy_out;
+    float* dump;
+    int dump_stage;                 // bring-up aid: 1 = dump the stage-1 result (C X^T as [v][h]) instead of the coefficients
+    int* status;
+    long long* trace;               // bring-up aid: clock64 at phase boundaries of CTA 0 / slot 0 (8 stamps per tile, 32 tiles)
+    FastDiv div_ms;
+};
+
+struct TScoreSmem {
+    static constexpr uint32_t BX_HALF = 2 * 64 * 128;              // data operand (hi or lo): 2 K-blocks x 64 rows x 128 B
+    static constexpr uint32_t SLOT_BYTES = 2 * BX_HALF;            // 32 KB per tile slot
+    static constexpr uint32_t C_HALF = 64 * 128;                   // stage-2 basis (hi or lo)
+    __host__ __device__ static constexpr uint32_t off_c(int nslot) { return nslot * SLOT_BYTES; }
+    __host__ __device__ static constexpr uint32_t off_ctrl(int nslot) { return off_c(nslot) + 2 * C_HALF; }
+    __host__ __device__ static constexpr uint32_t off_red(int nslot) { return off_ctrl(nslot) + 64; }
+    __host__ __device__ static constexpr uint32_t off_table(int nslot) { return off_red(nslot) + nslot * 1024; }
+    __host__ __device__ static constexpr uint32_t total(int nslot, uint32_t table_bytes) {
+        return off_table(nslot) + ((table_bytes + 15u) & ~15u);
+    }
+};
+
+constexpr int TSCORE_VEC = 2048;       // most float4 vectors a tile can hold (64x64: 2 maps)
+
+// NSLOT tile slots per CTA, WPS warps per slot (4: one warp per TMEM lane quarter; 8: two, splitting the columns)
+template <int NSLOT, int WPS>
+__global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 : 1) score_t_kernel(const TScoreArgs a) {
+    constexpr int TPS = 32 * WPS;                                  // threads per slot
+    constexpr int NT = TPS * NSLOT;                                // threads per CTA
+    constexpr int TSCORE_PF = TSCORE_VEC / TPS;                    // prefetch registers (float4) per thread
+    using S = TScoreSmem;
+    using namespace umma;
+    constexpr uint32_t TMEM_COLS = NSLOT == 1 ? 256 : 512;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t wg = warp / WPS, wtid = tid - wg * TPS;         // tile slot of this warp set, thread within it
+    const uint32_t swarp = warp - wg * WPS;                        // warp within the slot: lane quarter swarp & 3, column half swarp >> 2
+    uint8_t* bx_hi = smem + wg * S::SLOT_BYTES;
+    uint8_t* bx_lo = bx_hi + S::BX_HALF;
+    uint8_t* c_hi = smem + S::off_c(NSLOT);
+    uint8_t* c_lo = c_hi + S::C_HALF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_ctrl(NSLOT));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_ctrl(NSLOT) + 32);
+    float* red = reinterpret_cast<float*>(smem + S::off_red(NSLOT)) + wg * 256;   // [2 column halves][128 lanes]
+    const uint16_t* scat = reinterpret_cast<const uint16_t*>(smem + S::off_table(NSLOT));
+    uint64_t* bar = bars + wg;
+
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (tid == 0) atomicExch(a.status, DCTP_DEV_SMEM_ALIGN);
+        return;
+    }
+
+    // tiles of this slot: tile = first + i * stride
+    const int first = blockIdx.x * NSLOT + (int)wg, stride = gridDim.x * NSLOT;
+
+    // ---- the first tile's loads go out before anything else
+    float4 pf[TSCORE_PF];
+    uint32_t pf_full = 0;
+    auto prefetch = [&](int tile) {
+        const long long elem0 = static_cast<long long>(tile) * a.G * a.NN;
+        pf_full = static_cast<uint32_t>(min(static_cast<long long>(a.tile_vec), (a.total_elems - elem0) >> 2));
+        const float4* src = reinterpret_cast<const float4*>(a.x_dense + elem0) + wtid;
+#pragma unroll
+        for (int u = 0; u < TSCORE_PF; ++u)
+            if (wtid + u * TPS < pf_full) pf[u] = detail::ldg_stream(src + u * TPS);
+    };
+    if (first < a.num_tiles) prefetch(first);
+
+    // ---- one-time setup: zero the data operands, stage C and the scatter table, barriers, TMEM, A' into TMEM
+    for (uint32_t off = tid * 16; off < S::off_c(NSLOT); off += NT * 16)
+        *reinterpret_cast<uint4*>(smem + off) = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < 64 * 8; i += NT) {
+        const uint32_t n = i >> 3, c8 = i & 7;
+        const uint32_t off = detail::kmajor_off(n, c8 * 8, 64);
+        *reinterpret_cast<uint4*>(c_hi + off) = *reinterpret_cast<const uint4*>(a.c_hi + n * 64 + c8 * 8);
+        *reinterpret_cast<uint4*>(c_lo + off) = *reinterpret_cast<const uint4*>(a.c_lo + n * 64 + c8 * 8);
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.scatter);
+        uint4* dst = reinterpret_cast<uint4*>(smem + S::off_table(NSLOT));
+        for (uint32_t i = tid; i < (a.scatter_bytes + 15) / 16; i += NT) dst[i] = src[i];
+    }
+    if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (tid == 0) {
+        for (int s = 0; s < NSLOT; ++s) mbar_init(bars + s, 1);
+        mbar_init_fence();
+    }
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_bits = ((swarp & 3) * 32u) << 16;          // this warp's TMEM lane quarter
+    if (warp < 4) {                                                // A' = I_G (x) C_N, hi at columns [0,64), lo at [64,128)
+#pragma unroll 1
+        for (int part = 0; part < 8; ++part) {
+            const uint32_t* src = (part < 4 ? a.a_hi : a.a_lo) + tid * 64 + (part & 3) * 16;
+            uint32_t v[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 q = *reinterpret_cast<const uint4*>(src + 4 * i);
+                v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+            }
+            tmem_st16(tmem + ((warp * 32u) << 16) + part * 16, v);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+
+    const uint32_t slot_col = tmem + 128 + 128 * wg;               // this slot's TMEM columns
+    const uint32_t d_col = slot_col, a2_hi_col = slot_col + 64, a2_lo_col = slot_col + 96;
+    const uint32_t tmem_lane = lane_bits;                          // added to column addresses for ld/st
+
+    const uint64_t desc_k = make_smem_desc(0, 16, 1024, SWIZZLE_128B);
+    const uint32_t k_lo = static_cast<uint32_t>(desc_k);
+    const uint32_t lo_bx_hi = smem_u32(bx_hi) >> 4, lo_bx_lo = smem_u32(bx_lo) >> 4;
+    const uint32_t lo_c_hi = smem_u32(c_hi) >> 4, lo_c_lo = smem_u32(c_lo) >> 4;
+
+    // MMA issue is straight-line code (step counts are template parameters): a runtime loop costs ~100 cycles of
+    // dependent uniform-datapath work per MMA, three times the 32 cycles the tensor core needs for it.
+    auto issue_stage1 = [&]() {                                    // D1 = A' * Bx^T : A'hi*Bxhi + A'hi*Bxlo + A'lo*Bxhi
+        tc_fence_after_sync();
+        const uint32_t b_hi_lo = k_lo + lo_bx_hi, b_lo_lo = k_lo + lo_bx_lo;
+        switch (a.K1S) {
+            case 6: detail::issue_ts3<6>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
+            case 7: detail::issue_ts3<7>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
+            default: detail::issue_ts3<8>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
+        }
+        mma_commit(bar);
+    };
+    auto issue_stage2 = [&]() {                                    // D2 = A2 * C^T : A2hi*Chi + A2lo*Chi + A2hi*Clo
+        tc_fence_after_sync();
+        const uint32_t c_hi_lo = k_lo + lo_c_hi, c_lo_lo = k_lo + lo_c_lo;
+        switch (a.N1 >> 4) {
+            case 1: detail::issue_ts3<1>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
+            case 2: detail::issue_ts3<2>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
+            case 3: detail::issue_ts3<3>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
+            default: detail::issue_ts3<4>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
+        }
+        mma_commit(bar);
+    };
+
+    const uint32_t my_lane = (swarp & 3) * 32 + (tid & 31);        // TMEM lane of this thread
+    const uint32_t my_g = a.div_ms.div(my_lane);
+    const uint32_t my_v = my_lane - my_g * a.Ms;
+    constexpr int PARTS = WPS == 4 ? 2 : 1;                        // 32-column parts this warp handles
+    const int part0 = WPS == 4 ? 0 : (int)(swarp >> 2);
+    const bool lane_in_map = my_g < (uint32_t)a.G && my_v < (uint32_t)a.N;
+    const uint32_t bar_id = 1 + wg;
+    uint32_t phase = 0;
+    bool alive = true;
+
+    int trace_i = 0;
+    auto stamp = [&](int k) {
+        if (a.trace != nullptr && blockIdx.x == 0 && wtid == 0 && wg == 0 && trace_i < 32) a.trace[trace_i * 8 + k] = clock64();
+    };
+    for (int tile = first; tile < a.num_tiles; tile += stride) {
+        stamp(0);
+        const int map0 = tile * a.G;
+        const int maps_here = min(a.G, a.n_maps - map0);
+
+        // ---- stage 0: registers (prefetched) -> bf16 hi/lo -> data operand in shared memory
+#pragma unroll
+        for (int u = 0; u < TSCORE_PF; ++u)
+            if (wtid + u * TPS < pf_full) detail::Scatter<1>::st(bx_hi, bx_lo, scat[wtid + u * TPS], pf[u]);
+        stamp(1);
+        fence_async_smem();
+        tc_fence_before_sync();                                    // this warp's tcgen05.ld of the previous tile are done
+        named_bar_sync(bar_id, TPS);
+        stamp(2);
+        if (swarp == 0) {
+            if (elect_one()) issue_stage1();
+            __syncwarp();
+        }
+        if (tile + stride < a.num_tiles) prefetch(tile + stride);  // lands while the tensor core and the epilogues work
+        stamp(3);
+        if (!mbar_wait(bar, phase)) { alive = false; break; }
+        phase ^= 1;
+        tc_fence_after_sync();
+        stamp(4);
+
+        // ---- epilogue 1: D1 row (g,v) -> bf16 hi/lo pairs -> A2 in TMEM (columns h/2)
+#pragma unroll
+        for (int pi = 0; pi < PARTS; ++pi) {
+            const int part = part0 + pi;
+            if (part * 32 < a.N1) {
+                uint32_t r[2][16];
+                tmem_ld16(d_col + tmem_lane + part * 32, r[0]);
+                if (part * 32 + 16 < a.N1) tmem_ld16(d_col + tmem_lane + part * 32 + 16, r[1]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[1][i] = 0u;
+                }
+                tmem_ld_wait();
+                if (a.dump != nullptr && a.dump_stage == 1 && lane_in_map && (int)my_g < maps_here) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t h = part * 32 + i;
+                        if (h < (uint32_t)a.N) a.dump[(long long)(map0 + my_g) * a.NN + my_v * a.N + h] = __uint_as_float(r[i >> 4][i & 15]);
+                    }
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int p = 0; p < 16; ++p)
+                    split2(__uint_as_float(r[p >> 3][(p & 7) * 2]), __uint_as_float(r[p >> 3][(p & 7) * 2 + 1]), hi[p], lo[p]);
+                tmem_st16(a2_hi_col + tmem_lane + part * 16, hi);
+                tmem_st16(a2_lo_col + tmem_lane + part * 16, lo);
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        named_bar_sync(bar_id, TPS);
+        stamp(5);
+        if (swarp == 0) {
+            if (elect_one()) issue_stage2();
+            __syncwarp();
+        }
+        if (!mbar_wait(bar, phase)) { alive = false; break; }
+        phase ^= 1;
+        tc_fence_after_sync();
+        stamp(6);
+
+        // ---- epilogue 2: coefficients -> energy.  Lane = (g, v), column = u.
+        float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+        for (int pi = 0; pi < PARTS; ++pi) {
+            const int part = part0 + pi;
+            if (part * 32 < a.N1) {
+                uint32_t r[2][16];
+                tmem_ld16(d_col + tmem_lane + part * 32, r[0]);
+                if (part * 32 + 16 < a.N1) tmem_ld16(d_col + tmem_lane + part * 32 + 16, r[1]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[1][i] = 0u;
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float z0 = __uint_as_float(r[0][i]), z1 = __uint_as_float(r[1][i]);
+                    e0 = fmaf(z0, z0, e0);
+                    e1 = fmaf(z1, z1, e1);
+                }
+                if (a.dump != nullptr && a.dump_stage != 1 && lane_in_map && (int)my_g < maps_here) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t u = part * 32 + i;
+                        if (u < (uint32_t)a.N) a.dump[(long long)(map0 + my_g) * a.NN + u * a.N + my_v] = __uint_as_float(r[i >> 4][i & 15]);
+                    }
+                }
+            }
+        }
+        red[(WPS == 4 ? 0 : (swarp >> 2)) * 128 + my_lane] = e0 + e1;
+        named_bar_sync(bar_id, TPS);
+        {
+            // TPM threads per map, fixed summation order -> bit-reproducible per-map energy
+            const uint32_t t = wtid / a.TPM, sub = wtid % a.TPM;
+            const bool live = (int)t < maps_here && wtid < 128;
+            float s = 0.f;
+            if (live) {
+                const float* rp = red + t * a.Ms;
+                for (uint32_t v = sub; v < (uint32_t)a.N; v += a.TPM) s += WPS == 4 ? rp[v] : rp[v] + rp[128 + v];
+            }
+            for (uint32_t o = a.TPM >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (live && sub == 0) {
+                const int mm = map0 + (int)t;
+                atomicAdd(a.accum + (mm % a.c_count), (double)s);
+                if (a.energy_out) a.energy_out[mm] = s;
+            }
+        }
+        stamp(7);
+        ++trace_i;
+        // (`red` is rewritten only after two more barriers of this slot)
+    }
+
+    if (!alive && wtid == 0) atomicExch(a.status, DCTP_DEV_MMA_TIMEOUT);
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+}  // namespace dctp
