@@ -59,7 +59,8 @@ struct State {
     std::map<int, SimtBasis> simt;                     // N
     std::map<int, TBasis> tmem;                        // N
     int t_slots = 3;                                   // tile slots per CTA of the TMEM-operand kernel (DCTP_T_SLOTS=0 disables it)
-    int t_wps = 8;                                     // warps per tile slot (DCTP_T_WPS=4|8)
+    int t_wps = 4;                                     // warps per tile slot (DCTP_T_WPS=4|8)
+    bool t_all = false;
     int regs[2][6][2] = {};                            // registers/thread per (KP, load mode, prefetch) instantiation
     // scratch of dctp_score_host (grow-only)
     float* hx = nullptr; size_t hx_bytes = 0;
@@ -240,7 +241,8 @@ int ensure_init() {
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
     }
-    if (const char* e = std::getenv("DCTP_T_WPS")) g.t_wps = std::atoi(e) == 4 ? 4 : 8;
+    if (const char* e = std::getenv("DCTP_T_WPS")) g.t_wps = std::atoi(e) == 8 ? 8 : 4;
+    g.t_all = std::getenv("DCTP_T_ALL") != nullptr;
     if (const char* e = std::getenv("DCTP_T_SLOTS")) g.t_slots = std::atoi(e);
     if (g.t_slots < 0 || g.t_slots > 3) g.t_slots = 3;
     CUDA_TRY(cudaFuncSetAttribute(score_simt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMALL_SMEM));
@@ -270,7 +272,12 @@ int pick_vec(const float* x, long long stride_b, long long stride_c, int c_begin
 }
 
 // TMEM-operand kernel: dense tensors, N % 4 == 0, 16 <= N <= 64
-bool t_shape_ok(int N) { return g.t_slots > 0 && N >= 16 && N <= 64 && (N % 4) == 0; }
+// (measured on B200: it wins where a map fills the 64-column accumulator - 56x56 +12 %, 64x64 +17 % - and ties or loses
+//  below, where the smem-operand kernel packs several maps per lane group; DCTP_T_ALL=1 widens it to every N % 4 == 0 >= 16)
+bool t_shape_ok(int N) {
+    if (g.t_slots <= 0 || N > 64 || (N % 4) != 0) return false;
+    return g.t_all ? N >= 16 : N >= 52;
+}
 
 int launch_t(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
     TBasis basis;
