@@ -14,7 +14,7 @@ all-reduce, the finalise kernel and the segmented top-k, all inside the timed re
             feature maps of one batch, 9.2 GB per GPU: larger than L2, nothing to flush)
   e2e       images/s of complete importance generation through the public API: pinned host batch ->
             H2D -> cuDNN fp32 forward with all hooks live -> D2H of the running score sums, every step
-  roofline  dominant kernel (score_umma_kernel<64,0,1>: all 56^2/28^2 layers) timed with CUDA events
+  roofline  dominant kernel (largest share of the step; the 56^2 layers' kernel on ResNet-50) timed with CUDA events
             inside the timed region; algorithmic bytes = 4*H*W per scored map
   cpu_baseline  the oracle port of the reference hooks on this box's host cores, bounded sample
 
@@ -227,10 +227,18 @@ def run_ours(args):
     _lib.check(lib.dctp_check(None))
     session.reset()
 
-    # which launches belong to the dominant kernel: tensor-core kernel, KP=64, 128-bit loads
-    def is_dominant(a):
-        return a.shape[2] == a.shape[3] and a.shape[2] <= 64 and a.shape[2] % 4 == 0
-    dom = [i for i, a in enumerate(acts) if is_dominant(a)]
+    # which kernel a site's launch runs (mirrors the dispatch in csrc/dctp.cu for dense activations)
+    def kernel_of(a):
+        n = a.shape[2]
+        if a.shape[2] != a.shape[3] or n > 128:
+            return 'score_simt_kernel (fp32 CUDA cores)'
+        if n > 64:
+            return 'score_umma_kernel<128> (tcgen05, smem operands)'
+        if n % 4 == 0 and 52 <= n <= 64:
+            return 'score_t_kernel<3,4> (tcgen05, TMEM-resident operands, register prefetch)'
+        mode = 0 if n % 4 == 0 else 1 if n % 2 == 0 else 2
+        return 'score_umma_kernel<64,%d,1> (tcgen05 bf16x3, smem operands, register prefetch)' % mode
+    site_kernel = [kernel_of(a) for a in acts]
     ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in acts]
           for _ in range(args.steps)]
 
@@ -252,15 +260,26 @@ def run_ours(args):
     value = world * B * args.steps / (ms_total / 1e3)
 
     per_site_ms = [statistics.mean(ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(args.steps)) for i in range(len(acts))]
-    dom_ms = sum(per_site_ms[i] for i in dom)
-    dom_bytes = sum(site_bytes[i] for i in dom)
     hbm_peak, _, peak_kind = measured_peaks()
+    by_kernel = {}
+    for i, name in enumerate(site_kernel):
+        d = by_kernel.setdefault(name, {'launches_per_step': 0, 'ms_per_step': 0.0, 'bytes_per_step': 0})
+        d['launches_per_step'] += 1
+        d['ms_per_step'] += per_site_ms[i]
+        d['bytes_per_step'] += site_bytes[i]
+    for d in by_kernel.values():
+        d['GBps'] = d['bytes_per_step'] / (d['ms_per_step'] / 1e3) / 1e9
+        d['frac_hbm'] = d['GBps'] / hbm_peak
+    dom_name = max(by_kernel, key=lambda k: by_kernel[k]['ms_per_step'])       # dominant = largest share of the step
+    dom = [i for i, name in enumerate(site_kernel) if name == dom_name]
+    dom_ms = by_kernel[dom_name]['ms_per_step']
+    dom_bytes = by_kernel[dom_name]['bytes_per_step']
     achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(REPO, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get('dram_bytes_per_launch')
+            traffic = json.load(f).get(dom_name.split(' ')[0], {}).get('dram_bytes_per_launch')
     by_shape = {}
     for i, a in enumerate(acts):
         key = '%dx%dx%d' % (a.shape[1] if session.sites[i].variant != 'D' else 12, a.shape[2], a.shape[3])
@@ -328,9 +347,11 @@ def run_ours(args):
                        'compress_rate': wl['rate'], 'path': args.path, 'parallelism': 'batch-sharded x%d, 1 all-reduce per run' % world},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                         'traffic': traffic, 'peak_kind': peak_kind, 'kernel': 'score_umma_kernel<64,0,1> (tcgen05 bf16x3, dense 128-bit loads, register prefetch)',
+                         'traffic': traffic, 'peak_kind': peak_kind, 'kernel': dom_name,
+                         'share_of_step': dom_ms / (ms_total / args.steps),
                          'launches_per_step': len(dom), 'bytes_per_step': dom_bytes, 'ms_per_step': dom_ms},
             'hook_path_GBps': alg_bytes_step * args.steps / (ms_total / 1e3) / 1e9,
+            'by_kernel': {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in by_kernel.items()},
             'by_shape': shape_table,
             'clocks': clocks,
         }

@@ -8,8 +8,8 @@ import os
 
 from .build import LIB_PATH
 
-PATH_AUTO, PATH_UMMA, PATH_SIMT = 0, 1, 2
-PATHS = {'auto': PATH_AUTO, 'umma': PATH_UMMA, 'simt': PATH_SIMT}
+PATH_AUTO, PATH_UMMA, PATH_SIMT, PATH_TMEM = 0, 1, 2, 3
+PATHS = {'auto': PATH_AUTO, 'umma': PATH_UMMA, 'simt': PATH_SIMT, 'tmem': PATH_TMEM}
 
 OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_DEVICE = 0, -1, -2, -3, -4
 

@@ -340,7 +340,7 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
 
 template <int KP>
 int launch_umma(const float* x, int B, int N, long long stride_b, long long stride_c, int c_begin, int c_count,
-                double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
+                double* accum, float* energy_out, float* coeff_out, cudaStream_t stream, bool allow_t) {
     UmmaBasis basis;
     int rc = get_umma_basis(N, KP, basis);
     if (rc) return rc;
@@ -365,7 +365,7 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
     const float* first = x + static_cast<long long>(c_begin) * stride_c;
     const bool dense = basis.scatter != nullptr && stride_c == a.NN && (B == 1 || stride_b == static_cast<long long>(c_count) * a.NN) &&
                        (reinterpret_cast<uintptr_t>(first) % 16) == 0;
-    if (KP == 64 && dense && t_shape_ok(N))
+    if (KP == 64 && allow_t && dense && t_shape_ok(N))
         return launch_t(first, B, N, c_count, accum, energy_out, coeff_out, stream);
     int mode;
     if (dense) {
@@ -517,7 +517,7 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
     if (B < 0 || H < 1 || W < 1 || c_begin < 0 || c_count < 0 || stride_h < W)
         return fail(DCTP_E_INVALID, "dctp_score_accum: B=%d H=%d W=%d c_begin=%d c_count=%d stride_h=%lld", B, H, W, c_begin,
                     c_count, stride_h);
-    if (path != DCTP_PATH_AUTO && path != DCTP_PATH_UMMA && path != DCTP_PATH_SIMT) return fail(DCTP_E_INVALID, "unknown path %d", path);
+    if (path < DCTP_PATH_AUTO || path > DCTP_PATH_TMEM) return fail(DCTP_E_INVALID, "unknown path %d", path);
     if (B == 0 || c_count == 0) return DCTP_OK;                     // empty batch / empty window: nothing to add
     if (!x || !accum) return fail(DCTP_E_INVALID, "dctp_score_accum: null pointer");
     if (static_cast<long long>(B) * c_count > (1ll << 30)) return fail(DCTP_E_INVALID, "too many maps in one call");
@@ -528,8 +528,16 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
             if (!umma_shape_ok(H, W, stride_h))
                 return fail(DCTP_E_UNSUPPORTED, "UMMA path takes contiguous square maps of side <= 128 (got %dx%d, stride_h %lld)", H, W,
                             stride_h);
-            return H <= 64 ? launch_umma<64>(x, B, H, stride_b, stride_c, c_begin, c_count, accum, energy_out, coeff_out, s)
-                           : launch_umma<128>(x, B, H, stride_b, stride_c, c_begin, c_count, accum, energy_out, coeff_out, s);
+            return H <= 64 ? launch_umma<64>(x, B, H, stride_b, stride_c, c_begin, c_count, accum, energy_out, coeff_out, s, path == DCTP_PATH_AUTO)
+                           : launch_umma<128>(x, B, H, stride_b, stride_c, c_begin, c_count, accum, energy_out, coeff_out, s, false);
+        case DCTP_PATH_TMEM: {
+            const float* first = x + static_cast<long long>(c_begin) * stride_c;
+            const bool dense = stride_h == W && stride_c == static_cast<long long>(H) * W &&
+                               (B == 1 || stride_b == static_cast<long long>(c_count) * H * W) && (reinterpret_cast<uintptr_t>(first) % 16) == 0;
+            if (H != W || H < 16 || H > 64 || (H % 4) != 0 || !dense)
+                return fail(DCTP_E_UNSUPPORTED, "TMEM-operand path takes dense 16-B aligned square maps, side 16..64 multiple of 4 (got %dx%d)", H, W);
+            return launch_t(first, B, H, c_count, accum, energy_out, coeff_out, s);
+        }
         case DCTP_PATH_SIMT:
             return launch_simt(x, B, H, W, stride_b, stride_c, stride_h, c_begin, c_count, accum, energy_out, coeff_out, s);
         default:

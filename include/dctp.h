@@ -32,9 +32,10 @@ extern "C" {
 #define DCTP_E_DEVICE     -4      /* a kernel reported a fault in the device status word (tensor-core wait timed out) */
 
 /* kernel path for dctp_score_accum */
-#define DCTP_PATH_AUTO   0        /* tensor cores when the shape allows, CUDA cores otherwise */
-#define DCTP_PATH_UMMA   1        /* tcgen05/TMEM bf16x3 kernel; square maps, side <= 128, contiguous maps */
+#define DCTP_PATH_AUTO   0        /* the fastest tensor-core kernel the shape allows, CUDA cores otherwise */
+#define DCTP_PATH_UMMA   1        /* tcgen05/TMEM bf16x3 kernel, operands in shared memory; square maps, side <= 128, contiguous maps */
 #define DCTP_PATH_SIMT   2        /* fp32 CUDA-core kernels; any H x W, strided rows */
+#define DCTP_PATH_TMEM   3        /* tcgen05 kernel with TMEM-resident operands; dense square maps, side 16..64, side % 4 == 0 */
 
 int dctp_version(void);
 const char* dctp_last_error(void);

@@ -31,7 +31,8 @@ def rel_err(got, want):
     return np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
 
 
-UMMA_SIDES = [1, 2, 3, 4, 7, 8, 9, 10, 14, 16, 18, 20, 24, 28, 32, 36, 40, 48, 56, 64, 72, 80, 112, 128]
+UMMA_SIDES = [1, 2, 3, 4, 7, 8, 9, 10, 14, 16, 18, 20, 24, 28, 32, 36, 40, 48, 52, 56, 60, 64, 72, 80, 112, 128]
+TMEM_SIDES = [16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64]
 
 
 @pytest.mark.parametrize('n', UMMA_SIDES)
@@ -53,6 +54,26 @@ def test_energy_matches_float64_oracle(lib, cuda_device, n, path):
     # accum is the exact fp64 sum of the per-map fp32 energies
     # (the CUDA-core kernel for maps > 64 adds per-panel partials, so its two outputs agree to fp32 rounding only)
     np.testing.assert_allclose(got, en.astype(np.float64).sum(0), rtol=1e-12 if (path == 'umma' or n <= 64) else 1e-6)
+
+
+@pytest.mark.parametrize('n', TMEM_SIDES)
+def test_tmem_operand_kernel(lib, cuda_device, n):
+    """The TMEM-operand formulation (basis resident in TMEM, transposed stage 1) on every side it takes,
+    incl. many tiles per slot, a ragged last tile, and the coefficient dump."""
+    from scipy.fft import dctn
+    from dct_pruning_b200.ops import dct_energy
+    x = relu_maps((5, 131, n, n), seed=200 + n, dead_every=6)
+    acc, en, _ = dct_energy(x.to(cuda_device), path='tmem', want_energy=True)
+    want = port.energy_scipy64(x.numpy())
+    en = en.cpu().numpy()
+    live = want > 0
+    assert (en[~live] == 0).all()
+    assert rel_err(en[live], want[live]).max() < ENERGY_TOL
+    np.testing.assert_allclose(acc.cpu().numpy(), en.astype(np.float64).sum(0), rtol=1e-12)
+    small = relu_maps((1, 3, n, n), seed=300 + n)
+    _, _, co = dct_energy(small.to(cuda_device), path='tmem', want_coeff=True)
+    z = dctn(small.numpy().astype(np.float64), type=2, norm='ortho', axes=(-2, -1))
+    assert np.abs(co.cpu().numpy() - z).max() / np.abs(z).max() < 2e-5
 
 
 @pytest.mark.parametrize('n', [4, 7, 8, 10, 14, 20, 28, 40, 56, 64, 80, 128])
