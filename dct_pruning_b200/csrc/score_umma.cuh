@@ -183,6 +183,37 @@ template <> struct Scatter<4> {
     }
 };
 
+// three passes x KS k-steps of D (+)= A[smem] * B[smem]^T, straight-line (a runtime issue loop costs ~100 cycles of
+// dependent uniform-datapath work per MMA, three times what the tensor core needs for it).
+//   pass 0: A hi x B hi, pass 1: A lo x B hi, pass 2: A hi x B lo
+// MN_MAJOR_A: the A operand advances 2048 B per k-step (MN-major), else 32 B inside / one slab across 64-element K blocks.
+template <int KS, int KP, bool MN_MAJOR_A>
+__device__ __forceinline__ void issue_ss3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint64_t desc_a,
+                                          uint64_t desc_b, uint32_t idesc) {
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t la = pass == 1 ? a_lo : a_hi, lb = pass == 2 ? b_lo : b_hi;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+            umma::mma_bf16_ss(d, umma::desc_with_lo(desc_a, la + (MN_MAJOR_A ? ks * 128 : (ks >> 2) * 1024 + (ks & 3) * 2)),
+                              umma::desc_with_lo(desc_b, lb + (ks >> 2) * (KP * 8) + (ks & 3) * 2), idesc, (pass | ks) != 0);
+    }
+}
+template <int KP, bool MN_MAJOR_A>
+__device__ __forceinline__ void issue_ss3_n(int ks, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                            uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    switch (ks) {
+        case 1: issue_ss3<1, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
+        case 2: issue_ss3<2, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
+        case 3: issue_ss3<3, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
+        case 4: issue_ss3<4, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
+        case 5: if constexpr (KP > 64) issue_ss3<5, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
+        case 6: if constexpr (KP > 64) issue_ss3<6, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
+        case 7: if constexpr (KP > 64) issue_ss3<7, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
+        default: if constexpr (KP > 64) issue_ss3<8, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
+    }
+}
+
 }  // namespace detail
 
 template <int KP>
@@ -216,7 +247,6 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
     constexpr int VPE = MODE == LOAD_DENSE1 ? 1 : MODE == LOAD_DENSE2 ? 2 : 4;
     constexpr int VEC = MODE == LOAD_GEN4 ? 4 : MODE == LOAD_GEN2 ? 2 : 1;
     constexpr int NCHUNK = KP / 8;                                 // 8-column chunks of a D1 row
-    constexpr int KSTEPS = KP / 16;                                // most k-steps a stage can have
     constexpr int SLOTS = PF ? UMMA_PF_SLOTS : 1;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_hi = smem + S::OFF_A_HI;
@@ -290,41 +320,18 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
     const uint32_t lo_a_hi = smem_u32(a_hi) >> 4, lo_a_lo = smem_u32(a_lo) >> 4;
     const uint32_t lo_b_hi = smem_u32(b_hi) >> 4, lo_b_lo = smem_u32(b_lo) >> 4;
 
-    auto issue_stage1 = [&]() {                                    // one thread; D1 = A1 * B^T as hi*hi + lo*hi + hi*lo
+    auto issue_stage1 = [&]() {                                    // one elected thread; D1 = A1 * B^T
         tc_fence_after_sync();
-        uint32_t acc = 0;
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t la = pass == 1 ? lo_a_lo : lo_a_hi, lb = pass == 2 ? lo_b_lo : lo_b_hi;
-#pragma unroll
-            for (int ks = 0; ks < KSTEPS; ++ks) {
-                if (ks < a.K1) {
-                    mma_bf16_ss(tmem, desc_with_lo(desc_k, k_lo + la + (ks >> 2) * 1024 + (ks & 3) * 2),
-                                desc_with_lo(desc_k, k_lo + lb + (ks >> 2) * (KP * 8) + (ks & 3) * 2), a.idesc1, acc);
-                    acc = 1;
-                }
-            }
-        }
+        detail::issue_ss3_n<KP, false>(a.K1, tmem, k_lo + lo_a_hi, k_lo + lo_a_lo, k_lo + lo_b_hi, k_lo + lo_b_lo, desc_k, desc_k, a.idesc1);
         mma_commit(bar);
     };
     auto issue_stage2 = [&]() {                                    // per column group: D2 = A2_q * C^T
         tc_fence_after_sync();
 #pragma unroll 1
         for (uint32_t q = 0; q < (uint32_t)a.NQ; ++q) {
-            const uint32_t qoff = q * (a.a2_group_bytes >> 4), dcol = tmem + KP + q * a.N2;
-            uint32_t acc = 0;
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t la = (pass == 1 ? lo_a_lo : lo_a_hi) + qoff, lb = pass == 2 ? lo_b_lo : lo_b_hi;
-#pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                    if (ks < a.K2S) {
-                        mma_bf16_ss(dcol, desc_with_lo(desc_mn, mn_lo + la + ks * 128),
-                                    desc_with_lo(desc_k, k_lo + lb + (ks >> 2) * (KP * 8) + (ks & 3) * 2), a.idesc2, acc);
-                        acc = 1;
-                    }
-                }
-            }
+            const uint32_t qoff = q * (a.a2_group_bytes >> 4);
+            detail::issue_ss3_n<KP, true>(a.K2S, tmem + KP + q * a.N2, mn_lo + lo_a_hi + qoff, mn_lo + lo_a_lo + qoff, k_lo + lo_b_hi,
+                                          k_lo + lo_b_lo, desc_mn, desc_k, a.idesc2);
         }
         mma_commit(bar);
     };
@@ -430,7 +437,10 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         }
         fence_async_smem();
         __syncthreads();
-        if (tid == 0) issue_stage1();
+        if (warp == 0) {
+            if (elect_one()) issue_stage1();
+            __syncwarp();
+        }
         if constexpr (PF) {                                        // the following tile's loads go out now and land
             const int next = tile + (int)gridDim.x;                // while the tensor core and the epilogues work
             if (next < a.num_tiles) prefetch(next);
@@ -465,7 +475,10 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         tc_fence_before_sync();
         fence_async_smem();
         __syncthreads();
-        if (tid == 0) issue_stage2();
+        if (warp == 0) {
+            if (elect_one()) issue_stage2();
+            __syncwarp();
+        }
     };
     auto epilogue2 = [&](int tile) {
         const int map0 = tile * a.MT;
