@@ -44,8 +44,8 @@ struct UmmaBasis {                                                       // per 
 struct TBasis {                                                          // per N: operands of the TMEM-operand kernel
     uint32_t *a_hi = nullptr, *a_lo = nullptr;                           // [128][64] packed bf16 pairs of I_G (x) C_N
     uint16_t *c_hi = nullptr, *c_lo = nullptr;                           // [64][64] C_N zero padded
-    uint16_t* scatter = nullptr;                                         // [tile_vec]
-    int tile_vec = 0;
+    uint16_t* scatter = nullptr;                                         // [tile_vec][vpe]
+    int tile_vec = 0, vpe = 1;
 };
 struct SimtBasis { float* t = nullptr; };                               // [N x N], t[n*N + k] = C_N[k][n]
 
@@ -59,8 +59,8 @@ struct State {
     std::map<int, SimtBasis> simt;                     // N
     std::map<int, TBasis> tmem;                        // N
     int t_slots = 3;                                   // tile slots per CTA of the TMEM-operand kernel (DCTP_T_SLOTS=0 disables it)
-    int t_wps = 4;                                     // warps per tile slot (DCTP_T_WPS=4|8)
     bool t_all = false;
+    int t_auto_lo = 52;                                // smallest side AUTO routes to the TMEM-operand kernel (DCTP_T_LO)
     int regs[2][6][2] = {};                            // registers/thread per (KP, load mode, prefetch) instantiation
     // scratch of dctp_score_host (grow-only)
     float* hx = nullptr; size_t hx_bytes = 0;
@@ -125,10 +125,12 @@ int get_umma_basis(int N, int KP, UmmaBasis& out) {
     return DCTP_OK;
 }
 
+inline int t_n1max(int N) { return N <= 16 ? 16 : N <= 32 ? 32 : 64; }
+
 int get_t_basis(int N, TBasis& out) {
     auto it = g.tmem.find(N);
     if (it != g.tmem.end()) { out = it->second; return DCTP_OK; }
-    const int Ms = (N + 7) / 8 * 8, G = 128 / Ms, NN = N * N;
+    const int Ms = (N + 7) / 8 * 8, G = 128 / Ms, NN = N * N, rows = t_n1max(N);
     std::vector<uint32_t> ahi(128 * 64, 0), alo(128 * 64, 0);
     std::vector<uint16_t> chi(64 * 64, 0), clo(64 * 64, 0);
     for (int gI = 0; gI < G; ++gI)
@@ -143,12 +145,15 @@ int get_t_basis(int N, TBasis& out) {
     for (int u = 0; u < N; ++u)
         for (int h = 0; h < N; ++h) split_bf16(dct_coef(u, h, N), chi[u * 64 + h], clo[u * 64 + h]);
     TBasis b;
+    b.vpe = (N % 4 == 0) ? 1 : 2;
     b.tile_vec = G * NN / 4;
-    std::vector<uint16_t> tab(static_cast<size_t>(b.tile_vec) + 8, 0);
-    for (int v = 0; v < b.tile_vec; ++v) {
-        const int e = 4 * v, gI = e / NN, r = e % NN;
-        tab[v] = static_cast<uint16_t>(detail::kmajor_off(r / N, gI * N + r % N, 64));
-    }
+    const int step = 4 / b.vpe;
+    std::vector<uint16_t> tab(static_cast<size_t>(b.tile_vec) * b.vpe + 8, 0);
+    for (int v = 0; v < b.tile_vec; ++v)
+        for (int sI = 0; sI < b.vpe; ++sI) {
+            const int e = 4 * v + sI * step, gI = e / NN, r = e % NN;
+            tab[(size_t)v * b.vpe + sI] = static_cast<uint16_t>(detail::kmajor_off(r / N, gI * N + r % N, rows));
+        }
     CUDA_TRY(cudaMalloc(&b.a_hi, ahi.size() * 4));
     CUDA_TRY(cudaMalloc(&b.a_lo, alo.size() * 4));
     CUDA_TRY(cudaMalloc(&b.c_hi, chi.size() * 2));
@@ -234,17 +239,16 @@ int ensure_init() {
     if ((rc = setup_umma_all<64>(g.regs[0]))) return rc;
     if ((rc = setup_umma_all<128>(g.regs[1]))) return rc;
     {
-        const void* fns[] = {reinterpret_cast<const void*>(score_t_kernel<1, 4>), reinterpret_cast<const void*>(score_t_kernel<3, 4>),
-                             reinterpret_cast<const void*>(score_t_kernel<2, 8>), reinterpret_cast<const void*>(score_t_kernel<3, 8>)};
+        const void* fns[] = {reinterpret_cast<const void*>(score_t_kernel<64, 3, 1>), reinterpret_cast<const void*>(score_t_kernel<64, 3, 2>),
+                             reinterpret_cast<const void*>(score_t_kernel<32, 6, 1>), reinterpret_cast<const void*>(score_t_kernel<32, 6, 2>),
+                             reinterpret_cast<const void*>(score_t_kernel<16, 6, 1>), reinterpret_cast<const void*>(score_t_kernel<16, 6, 2>)};
         for (const void* fn : fns) {
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
     }
-    if (const char* e = std::getenv("DCTP_T_WPS")) g.t_wps = std::atoi(e) == 8 ? 8 : 4;
-    g.t_all = std::getenv("DCTP_T_ALL") != nullptr;
     if (const char* e = std::getenv("DCTP_T_SLOTS")) g.t_slots = std::atoi(e);
-    if (g.t_slots < 0 || g.t_slots > 3) g.t_slots = 3;
+    if (g.t_slots != 0) g.t_slots = 3;
     CUDA_TRY(cudaFuncSetAttribute(score_simt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMALL_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(score_simt_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CUDA_TRY(cudaMalloc(&g.status, sizeof(int)));
@@ -272,11 +276,13 @@ int pick_vec(const float* x, long long stride_b, long long stride_c, int c_begin
 }
 
 // TMEM-operand kernel: dense tensors, N % 4 == 0, 16 <= N <= 64
-// (measured on B200: it wins where a map fills the 64-column accumulator - 56x56 +12 %, 64x64 +17 % - and ties or loses
-//  below, where the smem-operand kernel packs several maps per lane group; DCTP_T_ALL=1 widens it to every N % 4 == 0 >= 16)
+// which maps the TMEM-operand kernel takes at all (dense, even side 10..64), and which ones AUTO gives it
+bool t_shape_supported(int N) { return N >= 10 && N <= 64 && (N % 2) == 0; }
 bool t_shape_ok(int N) {
-    if (g.t_slots <= 0 || N > 64 || (N % 4) != 0) return false;
-    return g.t_all ? N >= 16 : N >= 52;
+    if (g.t_slots <= 0 || !t_shape_supported(N)) return false;
+    // measured A/B on one B200 (tools/prof_one.py, [256,C,N,N]): 56x56 3.05 vs 2.65 TB/s, 64x64 3.43 vs 2.94; at 28x28 / 14x14 /
+    // 32x32 (6 slots) 2.36 / 2.03 / 1.79 vs 2.59 / 2.06 / 2.01 for the smem-operand kernel's multi-map packing
+    return g.t_all || N >= g.t_auto_lo;
 }
 
 int launch_t(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
@@ -293,10 +299,9 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
     a.K1S = (a.G * N + 15) / 16; a.N1 = (N + 15) / 16 * 16;
     a.TPM = pow2_floor(128 / a.G < 32 ? 128 / a.G : 32);
     a.idesc = umma::make_idesc_bf16(128, a.N1, false, false);
-    a.scatter = basis.scatter; a.scatter_bytes = static_cast<uint32_t>(basis.tile_vec) * 2u;
+    a.scatter = basis.scatter; a.scatter_bytes = static_cast<uint32_t>(basis.tile_vec) * basis.vpe * 2u;
     a.a_hi = basis.a_hi; a.a_lo = basis.a_lo; a.c_hi = basis.c_hi; a.c_lo = basis.c_lo;
     a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
-    if (const char* e = std::getenv("DCTP_T_DUMP_STAGE")) a.dump_stage = std::atoi(e);
     static long long* trace_buf = nullptr;
     const bool tracing = std::getenv("DCTP_T_TRACE") != nullptr;
     if (tracing) {
@@ -305,18 +310,23 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
         a.trace = trace_buf;
     }
     a.div_ms.set(a.Ms);
-    int ns = g.t_slots, wps = g.t_wps;
-    if (wps == 4 && ns == 2) ns = 3;                   // instantiated: (1,4) (3,4) (2,8) (3,8)
-    if (wps == 8 && ns == 1) ns = 2;
-    const size_t smem = TScoreSmem::total(ns, a.scatter_bytes);
-    const int ctas_per_sm = (ns == 1 && wps == 4) ? 2 : 1;
-    int grid = g.sm_count * ctas_per_sm;
+    const int n1max = t_n1max(N), ns = n1max == 64 ? 3 : 6;
+    const size_t smem = n1max == 64 ? TScoreSmem<64>::total(ns, a.scatter_bytes)
+                                    : n1max == 32 ? TScoreSmem<32>::total(ns, a.scatter_bytes) : TScoreSmem<16>::total(ns, a.scatter_bytes);
+    int grid = g.sm_count;
     const int need = (a.num_tiles + ns - 1) / ns;
     if (grid > need) grid = need;
-    if (wps == 4 && ns == 1) score_t_kernel<1, 4><<<grid, 128, smem, stream>>>(a);
-    else if (wps == 4) score_t_kernel<3, 4><<<grid, 384, smem, stream>>>(a);
-    else if (ns == 2) score_t_kernel<2, 8><<<grid, 512, smem, stream>>>(a);
-    else score_t_kernel<3, 8><<<grid, 768, smem, stream>>>(a);
+    const bool v2 = basis.vpe == 2;
+    if (n1max == 64) {
+        if (v2) score_t_kernel<64, 3, 2><<<grid, 384, smem, stream>>>(a);
+        else score_t_kernel<64, 3, 1><<<grid, 384, smem, stream>>>(a);
+    } else if (n1max == 32) {
+        if (v2) score_t_kernel<32, 6, 2><<<grid, 768, smem, stream>>>(a);
+        else score_t_kernel<32, 6, 1><<<grid, 768, smem, stream>>>(a);
+    } else {
+        if (v2) score_t_kernel<16, 6, 2><<<grid, 768, smem, stream>>>(a);
+        else score_t_kernel<16, 6, 1><<<grid, 768, smem, stream>>>(a);
+    }
     if (tracing) {
         long long h[256];
         CUDA_TRY(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
@@ -534,8 +544,8 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
             const float* first = x + static_cast<long long>(c_begin) * stride_c;
             const bool dense = stride_h == W && stride_c == static_cast<long long>(H) * W &&
                                (B == 1 || stride_b == static_cast<long long>(c_count) * H * W) && (reinterpret_cast<uintptr_t>(first) % 16) == 0;
-            if (H != W || H < 16 || H > 64 || (H % 4) != 0 || !dense)
-                return fail(DCTP_E_UNSUPPORTED, "TMEM-operand path takes dense 16-B aligned square maps, side 16..64 multiple of 4 (got %dx%d)", H, W);
+            if (H != W || !t_shape_supported(H) || !dense)
+                return fail(DCTP_E_UNSUPPORTED, "TMEM-operand path takes dense 16-B aligned square maps, even side 10..64 (got %dx%d)", H, W);
             return launch_t(first, B, H, c_count, accum, energy_out, coeff_out, s);
         }
         case DCTP_PATH_SIMT:

@@ -1,4 +1,4 @@
-// Fused DCT-score hook kernel, TMEM-operand formulation (maps of side 16..64, N % 4 == 0, dense tensors).
+// Fused DCT-score hook kernel, TMEM-operand formulation (dense tensors, even map side 10..64).
 //
 // Same contract as score_umma.cuh (/root/reference/utils/common.py:262-277: per-(image,channel)
 // orthonormal 2-D DCT-II energy, summed per channel), re-arranged because ncu shows the K-major/MN-major
@@ -20,8 +20,10 @@
 // The price: the block-diagonal A' wastes a factor G of stage-1 tensor work (1056 tensor cycles per 25 KB at
 // 56x56 vs 768), still below the HBM time (1080 cycles at the measured 6.55 TB/s).
 //
-// TMEM: [0,128) A' (hi | lo, written once), then per tile slot 128 columns: D (64, D2 re-uses D1) | A2 hi (32) | A2 lo (32).
-// One CTA runs NSLOT independent tile slots, one warpgroup (4 warps = 128 TMEM lanes) each, sharing A' and C.
+// TMEM: [0,128) A' (hi | lo, written once), then per tile slot 2*N1MAX columns: D (N1MAX, D2 re-uses D1) |
+// A2 hi (N1MAX/2) | A2 lo (N1MAX/2).  One CTA runs NSLOT independent tile slots, one warpgroup (4 warps = 128
+// TMEM lanes) each, sharing A' and C: 3 slots for maps up to 64 wide, 6 for maps up to 32 or 16 wide (the
+// per-tile dependency chain is what bounds this kernel, so smaller tiles get more slots).
 #pragma once
 #include "score_umma.cuh"
 
@@ -29,8 +31,9 @@ namespace dctp {
 
 namespace detail {
 // three passes x KS k-steps of D (+)= A[tmem] * B[smem]^T, fully unrolled.  Pass p reads the TMEM operand at
-// column a_p + 8*ks and the K-major shared-memory operand whose descriptor low word is b_p (+ k-step offset).
-template <int KS>
+// column a_p + 8*ks and the K-major shared-memory operand whose descriptor low word is b_p (+ k-step offset;
+// KB16 = distance between 64-element K blocks in 16-byte units).
+template <int KS, int KB16>
 __device__ __forceinline__ void issue_ts3(uint32_t d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b0, uint32_t b1, uint32_t b2,
                                           uint64_t desc, uint32_t idesc) {
 #pragma unroll
@@ -39,7 +42,7 @@ __device__ __forceinline__ void issue_ts3(uint32_t d, uint32_t a0, uint32_t a1, 
         const uint32_t bl = pass == 0 ? b0 : pass == 1 ? b1 : b2;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks)
-            umma::mma_bf16_ts(d, ac + 8 * ks, umma::desc_with_lo(desc, bl + (ks >> 2) * 512 + (ks & 3) * 2), idesc,
+            umma::mma_bf16_ts(d, ac + 8 * ks, umma::desc_with_lo(desc, bl + (ks >> 2) * KB16 + (ks & 3) * 2), idesc,
                               (pass | ks) != 0);
     }
 }
@@ -56,7 +59,7 @@ struct TScoreArgs {
     int N1;                         // N rounded up to 16: MMA N of both stages, contraction length of stage 2
     int TPM;                        // threads per map in the final reduction
     uint32_t idesc;                 // M = 128, N = N1, bf16 x bf16 -> f32, K-major B
-    const uint16_t* scatter;        // [tile_vec] byte offset of each float4 (as 4 bf16) in the K-major data operand
+    const uint16_t* scatter;        // [tile_vec][VPE] byte offsets of each float4's pieces in the K-major data operand
     uint32_t scatter_bytes;
     const uint32_t* a_hi;           // [128][64] packed bf16 pairs of A' = I_G (x) C_N (row (g,v), column pair (g',w)/2)
     const uint32_t* a_lo;
@@ -65,36 +68,39 @@ struct TScoreArgs {
     double* accum;
     float* energy_out;
     float* dump;
-    int dump_stage;                 // bring-up aid: 1 = dump the stage-1 result (C X^T as [v][h]) instead of the coefficients
     int* status;
     long long* trace;               // bring-up aid: clock64 at phase boundaries of CTA 0 / slot 0 (8 stamps per tile, 32 tiles)
     FastDiv div_ms;
 };
 
+template <int N1MAX>
 struct TScoreSmem {
-    static constexpr uint32_t BX_HALF = 2 * 64 * 128;              // data operand (hi or lo): 2 K-blocks x 64 rows x 128 B
-    static constexpr uint32_t SLOT_BYTES = 2 * BX_HALF;            // 32 KB per tile slot
+    static constexpr uint32_t BX_HALF = 2 * N1MAX * 128;           // data operand (hi or lo): 2 K-blocks x N1MAX rows x 128 B
+    static constexpr uint32_t SLOT_BYTES = 2 * BX_HALF;
     static constexpr uint32_t C_HALF = 64 * 128;                   // stage-2 basis (hi or lo)
     __host__ __device__ static constexpr uint32_t off_c(int nslot) { return nslot * SLOT_BYTES; }
     __host__ __device__ static constexpr uint32_t off_ctrl(int nslot) { return off_c(nslot) + 2 * C_HALF; }
-    __host__ __device__ static constexpr uint32_t off_red(int nslot) { return off_ctrl(nslot) + 64; }
-    __host__ __device__ static constexpr uint32_t off_table(int nslot) { return off_red(nslot) + nslot * 1024; }
+    __host__ __device__ static constexpr uint32_t off_red(int nslot) { return off_ctrl(nslot) + 128; }
+    __host__ __device__ static constexpr uint32_t off_table(int nslot) { return off_red(nslot) + nslot * 512; }
     __host__ __device__ static constexpr uint32_t total(int nslot, uint32_t table_bytes) {
         return off_table(nslot) + ((table_bytes + 15u) & ~15u);
     }
 };
 
-constexpr int TSCORE_VEC = 2048;       // most float4 vectors a tile can hold (64x64: 2 maps)
-
-// NSLOT tile slots per CTA, WPS warps per slot (4: one warp per TMEM lane quarter; 8: two, splitting the columns)
-template <int NSLOT, int WPS>
-__global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 : 1) score_t_kernel(const TScoreArgs a) {
-    constexpr int TPS = 32 * WPS;                                  // threads per slot
-    constexpr int NT = TPS * NSLOT;                                // threads per CTA
-    constexpr int TSCORE_PF = TSCORE_VEC / TPS;                    // prefetch registers (float4) per thread
-    using S = TScoreSmem;
+// N1MAX: widest accumulator a slot holds (64 / 32 / 16 columns); NSLOT tile slots per CTA (one warpgroup each);
+// VPE: scatter pieces per float4 (1: N % 4 == 0, one 8-byte store; 2: N even, two 4-byte stores)
+template <int N1MAX, int NSLOT, int VPE>
+__global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArgs a) {
+    using S = TScoreSmem<N1MAX>;
     using namespace umma;
-    constexpr uint32_t TMEM_COLS = NSLOT == 1 ? 256 : 512;
+    constexpr int WPS = 4, TPS = 128;                              // one warpgroup (= all 128 TMEM lanes) per slot
+    constexpr int NT = TPS * NSLOT;
+    constexpr int TSCORE_PF = N1MAX == 64 ? 16 : N1MAX == 32 ? 8 : 4;   // prefetch registers (float4) per thread: a full tile
+    constexpr uint32_t SLOT_COLS = 2 * N1MAX;
+    constexpr uint32_t TMEM_COLS = 512;
+    static_assert(128 + NSLOT * SLOT_COLS <= TMEM_COLS, "TMEM budget");
+    constexpr int KB16 = N1MAX * 8;                                // 64-element K block of the data operand, in 16-byte units
+    using Entry = typename detail::Scatter<VPE>::Entry;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t wg = warp / WPS, wtid = tid - wg * TPS;         // tile slot of this warp set, thread within it
@@ -104,9 +110,9 @@ __global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 :
     uint8_t* c_hi = smem + S::off_c(NSLOT);
     uint8_t* c_lo = c_hi + S::C_HALF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_ctrl(NSLOT));
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_ctrl(NSLOT) + 32);
-    float* red = reinterpret_cast<float*>(smem + S::off_red(NSLOT)) + wg * 256;   // [2 column halves][128 lanes]
-    const uint16_t* scat = reinterpret_cast<const uint16_t*>(smem + S::off_table(NSLOT));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_ctrl(NSLOT) + 64);
+    float* red = reinterpret_cast<float*>(smem + S::off_red(NSLOT)) + wg * 128;
+    const Entry* scat = reinterpret_cast<const Entry*>(smem + S::off_table(NSLOT));
     uint64_t* bar = bars + wg;
 
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -173,8 +179,8 @@ __global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 :
     __syncthreads();
     tc_fence_after_sync();
 
-    const uint32_t slot_col = tmem + 128 + 128 * wg;               // this slot's TMEM columns
-    const uint32_t d_col = slot_col, a2_hi_col = slot_col + 64, a2_lo_col = slot_col + 96;
+    const uint32_t slot_col = tmem + 128 + SLOT_COLS * wg;         // this slot's TMEM columns
+    const uint32_t d_col = slot_col, a2_hi_col = slot_col + N1MAX, a2_lo_col = slot_col + N1MAX + N1MAX / 2;
     const uint32_t tmem_lane = lane_bits;                          // added to column addresses for ld/st
 
     const uint64_t desc_k = make_smem_desc(0, 16, 1024, SWIZZLE_128B);
@@ -188,9 +194,10 @@ __global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 :
         tc_fence_after_sync();
         const uint32_t b_hi_lo = k_lo + lo_bx_hi, b_lo_lo = k_lo + lo_bx_lo;
         switch (a.K1S) {
-            case 6: detail::issue_ts3<6>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
-            case 7: detail::issue_ts3<7>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
-            default: detail::issue_ts3<8>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
+            case 5: detail::issue_ts3<5, KB16>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
+            case 6: detail::issue_ts3<6, KB16>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
+            case 7: detail::issue_ts3<7, KB16>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
+            default: detail::issue_ts3<8, KB16>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
         }
         mma_commit(bar);
     };
@@ -198,10 +205,10 @@ __global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 :
         tc_fence_after_sync();
         const uint32_t c_hi_lo = k_lo + lo_c_hi, c_lo_lo = k_lo + lo_c_lo;
         switch (a.N1 >> 4) {
-            case 1: detail::issue_ts3<1>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
-            case 2: detail::issue_ts3<2>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
-            case 3: detail::issue_ts3<3>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
-            default: detail::issue_ts3<4>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
+            case 1: detail::issue_ts3<1, 0>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
+            case 2: if constexpr (N1MAX >= 32) detail::issue_ts3<2, 0>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
+            case 3: if constexpr (N1MAX >= 64) detail::issue_ts3<3, 0>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
+            default: if constexpr (N1MAX >= 64) detail::issue_ts3<4, 0>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
         }
         mma_commit(bar);
     };
@@ -209,8 +216,8 @@ __global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 :
     const uint32_t my_lane = (swarp & 3) * 32 + (tid & 31);        // TMEM lane of this thread
     const uint32_t my_g = a.div_ms.div(my_lane);
     const uint32_t my_v = my_lane - my_g * a.Ms;
-    constexpr int PARTS = WPS == 4 ? 2 : 1;                        // 32-column parts this warp handles
-    const int part0 = WPS == 4 ? 0 : (int)(swarp >> 2);
+    constexpr int PARTS = N1MAX >= 64 ? 2 : 1;                     // 32-column parts of an accumulator row
+    const int part0 = 0;
     const bool lane_in_map = my_g < (uint32_t)a.G && my_v < (uint32_t)a.N;
     const uint32_t bar_id = 1 + wg;
     uint32_t phase = 0;
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 :
         // ---- stage 0: registers (prefetched) -> bf16 hi/lo -> data operand in shared memory
 #pragma unroll
         for (int u = 0; u < TSCORE_PF; ++u)
-            if (wtid + u * TPS < pf_full) detail::Scatter<1>::st(bx_hi, bx_lo, scat[wtid + u * TPS], pf[u]);
+            if (wtid + u * TPS < pf_full) detail::Scatter<VPE>::st(bx_hi, bx_lo, scat[wtid + u * TPS], pf[u]);
         stamp(1);
         fence_async_smem();
         tc_fence_before_sync();                                    // this warp's tcgen05.ld of the previous tile are done
@@ -252,25 +259,23 @@ __global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 :
             if (part * 32 < a.N1) {
                 uint32_t r[2][16];
                 tmem_ld16(d_col + tmem_lane + part * 32, r[0]);
-                if (part * 32 + 16 < a.N1) tmem_ld16(d_col + tmem_lane + part * 32 + 16, r[1]);
+                if (N1MAX >= 32 && part * 32 + 16 < a.N1) tmem_ld16(d_col + tmem_lane + part * 32 + 16, r[1]);
                 else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) r[1][i] = 0u;
                 }
                 tmem_ld_wait();
-                if (a.dump != nullptr && a.dump_stage == 1 && lane_in_map && (int)my_g < maps_here) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const uint32_t h = part * 32 + i;
-                        if (h < (uint32_t)a.N) a.dump[(long long)(map0 + my_g) * a.NN + my_v * a.N + h] = __uint_as_float(r[i >> 4][i & 15]);
-                    }
-                }
                 uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int p = 0; p < 16; ++p)
+                for (int p = 0; p < (N1MAX >= 32 ? 16 : 8); ++p)
                     split2(__uint_as_float(r[p >> 3][(p & 7) * 2]), __uint_as_float(r[p >> 3][(p & 7) * 2 + 1]), hi[p], lo[p]);
-                tmem_st16(a2_hi_col + tmem_lane + part * 16, hi);
-                tmem_st16(a2_lo_col + tmem_lane + part * 16, lo);
+                if constexpr (N1MAX >= 32) {
+                    tmem_st16(a2_hi_col + tmem_lane + part * 16, hi);
+                    tmem_st16(a2_lo_col + tmem_lane + part * 16, lo);
+                } else {
+                    tmem_st8(a2_hi_col + tmem_lane, hi);
+                    tmem_st8(a2_lo_col + tmem_lane, lo);
+                }
             }
         }
         tmem_st_wait();
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 :
             if (part * 32 < a.N1) {
                 uint32_t r[2][16];
                 tmem_ld16(d_col + tmem_lane + part * 32, r[0]);
-                if (part * 32 + 16 < a.N1) tmem_ld16(d_col + tmem_lane + part * 32 + 16, r[1]);
+                if (N1MAX >= 32 && part * 32 + 16 < a.N1) tmem_ld16(d_col + tmem_lane + part * 32 + 16, r[1]);
                 else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) r[1][i] = 0u;
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 :
                     e0 = fmaf(z0, z0, e0);
                     e1 = fmaf(z1, z1, e1);
                 }
-                if (a.dump != nullptr && a.dump_stage != 1 && lane_in_map && (int)my_g < maps_here) {
+                if (a.dump != nullptr && lane_in_map && (int)my_g < maps_here) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const uint32_t u = part * 32 + i;
@@ -315,16 +320,16 @@ __global__ void __launch_bounds__(32 * WPS * NSLOT, NSLOT == 1 && WPS == 4 ? 2 :
                 }
             }
         }
-        red[(WPS == 4 ? 0 : (swarp >> 2)) * 128 + my_lane] = e0 + e1;
+        red[wtid] = e0 + e1;
         named_bar_sync(bar_id, TPS);
         {
             // TPM threads per map, fixed summation order -> bit-reproducible per-map energy
             const uint32_t t = wtid / a.TPM, sub = wtid % a.TPM;
-            const bool live = (int)t < maps_here && wtid < 128;
+            const bool live = (int)t < maps_here;
             float s = 0.f;
             if (live) {
                 const float* rp = red + t * a.Ms;
-                for (uint32_t v = sub; v < (uint32_t)a.N; v += a.TPM) s += WPS == 4 ? rp[v] : rp[v] + rp[128 + v];
+                for (uint32_t v = sub; v < (uint32_t)a.N; v += a.TPM) s += rp[v];
             }
             for (uint32_t o = a.TPM >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (live && sub == 0) {

@@ -32,7 +32,7 @@ def rel_err(got, want):
 
 
 UMMA_SIDES = [1, 2, 3, 4, 7, 8, 9, 10, 14, 16, 18, 20, 24, 28, 32, 36, 40, 48, 52, 56, 60, 64, 72, 80, 112, 128]
-TMEM_SIDES = [16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64]
+TMEM_SIDES = [10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 34, 36, 40, 44, 48, 50, 52, 56, 60, 62, 64]
 
 
 @pytest.mark.parametrize('n', UMMA_SIDES)

@@ -15,7 +15,6 @@ iters = int(sys.argv[6]) if len(sys.argv) > 6 else 5
 dev = torch.device('cuda', 0)
 lib = _lib.load()
 _lib.check(lib.dctp_init())
-print('occupancy kp64:', [lib.dctp_occupancy(64, m) for m in range(6)], 'kp128:', [lib.dctp_occupancy(128, m) for m in range(6)])
 x = torch.relu(torch.randn(B, C, H, W, device=dev))
 acc = torch.zeros(C, dtype=torch.float64, device=dev)
 for _ in range(2):
