@@ -12,6 +12,7 @@
 
 #include "../../include/dctp.h"
 #include "score_simt.cuh"
+#include "score_large.cuh"
 #include "score_tmem.cuh"
 #include "score_umma.cuh"
 #include "topk.cuh"
@@ -47,6 +48,7 @@ struct TBasis {                                                          // per 
     uint16_t* scatter = nullptr;                                         // [tile_vec][vpe]
     int tile_vec = 0, vpe = 1;
 };
+struct LargeBasis { uint16_t *hi = nullptr, *lo = nullptr; int NP = 0; };   // [NP][NP] C_N zero padded, NP = N rounded up to 64
 struct SimtBasis { float* t = nullptr; };                               // [N x N], t[n*N + k] = C_N[k][n]
 
 struct State {
@@ -58,6 +60,7 @@ struct State {
     std::map<std::pair<int, int>, UmmaBasis> umma;     // (N, KP)
     std::map<int, SimtBasis> simt;                     // N
     std::map<int, TBasis> tmem;                        // N
+    std::map<int, LargeBasis> large;                   // N
     int t_slots = 3;                                   // tile slots per CTA of the TMEM-operand kernel (DCTP_T_SLOTS=0 disables it)
     bool t_all = false;
     int t_auto_lo = 52;                                // smallest side AUTO routes to the TMEM-operand kernel (DCTP_T_LO)
@@ -169,6 +172,23 @@ int get_t_basis(int N, TBasis& out) {
     return DCTP_OK;
 }
 
+int get_large_basis(int N, LargeBasis& out) {
+    auto it = g.large.find(N);
+    if (it != g.large.end()) { out = it->second; return DCTP_OK; }
+    LargeBasis b;
+    b.NP = (N + 63) / 64 * 64;
+    std::vector<uint16_t> hi(static_cast<size_t>(b.NP) * b.NP, 0), lo(hi.size(), 0);
+    for (int k = 0; k < N; ++k)
+        for (int n = 0; n < N; ++n) split_bf16(dct_coef(k, n, N), hi[(size_t)k * b.NP + n], lo[(size_t)k * b.NP + n]);
+    CUDA_TRY(cudaMalloc(&b.hi, hi.size() * 2));
+    CUDA_TRY(cudaMalloc(&b.lo, lo.size() * 2));
+    CUDA_TRY(cudaMemcpy(b.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    g.large[N] = b;
+    out = b;
+    return DCTP_OK;
+}
+
 int get_simt_basis(int N, SimtBasis& out) {
     auto it = g.simt.find(N);
     if (it != g.simt.end()) { out = it->second; return DCTP_OK; }
@@ -249,6 +269,7 @@ int ensure_init() {
     }
     if (const char* e = std::getenv("DCTP_T_SLOTS")) g.t_slots = std::atoi(e);
     if (g.t_slots != 0) g.t_slots = 3;
+    CUDA_TRY(cudaFuncSetAttribute(score_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LargeSmem::TOTAL));
     CUDA_TRY(cudaFuncSetAttribute(score_simt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMALL_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(score_simt_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CUDA_TRY(cudaMalloc(&g.status, sizeof(int)));
@@ -276,6 +297,29 @@ int pick_vec(const float* x, long long stride_b, long long stride_c, int c_begin
 }
 
 // TMEM-operand kernel: dense tensors, N % 4 == 0, 16 <= N <= 64
+// large-map tensor-core kernel: dense square maps, 128 < N <= 320, N % 16 == 0
+bool large_shape_ok(int H, int W, long long stride_h) { return H == W && H > 128 && H <= 320 && (H % 16) == 0 && stride_h == W; }
+
+int launch_large(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
+    LargeBasis basis;
+    int rc = get_large_basis(N, basis);
+    if (rc) return rc;
+    LargeScoreArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.x_dense = first; a.n_maps = B * c_count; a.c_count = c_count;
+    a.N = N; a.NP = basis.NP; a.NVC = (N + 127) / 128;
+    a.NU = N <= 160 ? N : ((N / 2 + 15) / 16) * 16; a.NUC = N <= 160 ? 1 : 2;
+    a.n_items = a.n_maps * a.NVC;
+    a.c_hi = basis.hi; a.c_lo = basis.lo;
+    a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
+    if (energy_out) CUDA_TRY(cudaMemsetAsync(energy_out, 0, sizeof(float) * a.n_maps, stream));
+    int grid = g.sm_count < a.n_items ? g.sm_count : a.n_items;
+    score_large_kernel<<<grid, 128, LargeSmem::TOTAL, stream>>>(a);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    return DCTP_OK;
+}
+
 // which maps the TMEM-operand kernel takes at all (dense, even side 10..64), and which ones AUTO gives it
 bool t_shape_supported(int N) { return N >= 10 && N <= 64 && (N % 2) == 0; }
 bool t_shape_ok(int N) {
@@ -449,6 +493,7 @@ int launch_simt(const float* x, int B, int H, int W, long long stride_b, long lo
 int resolve_path(int path, int H, int W, long long stride_h) {
     if (path == DCTP_PATH_AUTO) {
         if (umma_shape_ok(H, W, stride_h)) return DCTP_PATH_UMMA;
+        if (large_shape_ok(H, W, stride_h)) return DCTP_PATH_LARGE;
         return DCTP_PATH_SIMT;
     }
     return path;
@@ -472,10 +517,11 @@ int dctp_shutdown(void) {
     if (!g.ready) return DCTP_OK;
     for (auto& kv : g.umma) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); cudaFree(kv.second.scatter); }
     for (auto& kv : g.simt) cudaFree(kv.second.t);
+    for (auto& kv : g.large) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
     for (auto& kv : g.tmem) {
         cudaFree(kv.second.a_hi); cudaFree(kv.second.a_lo); cudaFree(kv.second.c_hi); cudaFree(kv.second.c_lo); cudaFree(kv.second.scatter);
     }
-    g.umma.clear(); g.simt.clear(); g.tmem.clear();
+    g.umma.clear(); g.simt.clear(); g.tmem.clear(); g.large.clear();
     cudaFree(g.status); cudaFree(g.hx); cudaFree(g.hacc); cudaFree(g.hout);
     g = State();
     return DCTP_OK;
@@ -513,6 +559,10 @@ int dctp_prepare(int H, int W) {
         UmmaBasis b;
         return get_umma_basis(H, H <= 64 ? 64 : 128, b);
     }
+    if (large_shape_ok(H, W, W)) {
+        LargeBasis lb;
+        if ((rc = get_large_basis(H, lb))) return rc;
+    }
     SimtBasis b;
     if ((rc = get_simt_basis(H, b))) return rc;
     return get_simt_basis(W, b);
@@ -527,7 +577,7 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
     if (B < 0 || H < 1 || W < 1 || c_begin < 0 || c_count < 0 || stride_h < W)
         return fail(DCTP_E_INVALID, "dctp_score_accum: B=%d H=%d W=%d c_begin=%d c_count=%d stride_h=%lld", B, H, W, c_begin,
                     c_count, stride_h);
-    if (path < DCTP_PATH_AUTO || path > DCTP_PATH_TMEM) return fail(DCTP_E_INVALID, "unknown path %d", path);
+    if (path < DCTP_PATH_AUTO || path > DCTP_PATH_LARGE) return fail(DCTP_E_INVALID, "unknown path %d", path);
     if (B == 0 || c_count == 0) return DCTP_OK;                     // empty batch / empty window: nothing to add
     if (!x || !accum) return fail(DCTP_E_INVALID, "dctp_score_accum: null pointer");
     if (static_cast<long long>(B) * c_count > (1ll << 30)) return fail(DCTP_E_INVALID, "too many maps in one call");
@@ -547,6 +597,17 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
             if (H != W || !t_shape_supported(H) || !dense)
                 return fail(DCTP_E_UNSUPPORTED, "TMEM-operand path takes dense 16-B aligned square maps, even side 10..64 (got %dx%d)", H, W);
             return launch_t(first, B, H, c_count, accum, energy_out, coeff_out, s);
+        }
+        case DCTP_PATH_LARGE: {
+            const float* first = x + static_cast<long long>(c_begin) * stride_c;
+            const bool dense = stride_c == static_cast<long long>(H) * W && (B == 1 || stride_b == static_cast<long long>(c_count) * H * W) &&
+                               (reinterpret_cast<uintptr_t>(first) % 16) == 0;
+            if (!large_shape_ok(H, W, stride_h) || !dense) {
+                if (path == DCTP_PATH_AUTO)              // windows / strided batches of large maps: CUDA cores
+                    return launch_simt(x, B, H, W, stride_b, stride_c, stride_h, c_begin, c_count, accum, energy_out, coeff_out, s);
+                return fail(DCTP_E_UNSUPPORTED, "large-map path takes dense 16-B aligned square maps, side 144..320 multiple of 16 (got %dx%d)", H, W);
+            }
+            return launch_large(first, B, H, c_count, accum, energy_out, coeff_out, s);
         }
         case DCTP_PATH_SIMT:
             return launch_simt(x, B, H, W, stride_b, stride_c, stride_h, c_begin, c_count, accum, energy_out, coeff_out, s);

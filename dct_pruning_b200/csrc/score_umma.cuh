@@ -189,28 +189,28 @@ template <> struct Scatter<4> {
 // MN_MAJOR_A: the A operand advances 2048 B per k-step (MN-major), else 32 B inside / one slab across 64-element K blocks.
 template <int KS, int KP, bool MN_MAJOR_A>
 __device__ __forceinline__ void issue_ss3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint64_t desc_a,
-                                          uint64_t desc_b, uint32_t idesc) {
+                                          uint64_t desc_b, uint32_t idesc, bool acc0 = false) {
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
         const uint32_t la = pass == 1 ? a_lo : a_hi, lb = pass == 2 ? b_lo : b_hi;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks)
             umma::mma_bf16_ss(d, umma::desc_with_lo(desc_a, la + (MN_MAJOR_A ? ks * 128 : (ks >> 2) * 1024 + (ks & 3) * 2)),
-                              umma::desc_with_lo(desc_b, lb + (ks >> 2) * (KP * 8) + (ks & 3) * 2), idesc, (pass | ks) != 0);
+                              umma::desc_with_lo(desc_b, lb + (ks >> 2) * (KP * 8) + (ks & 3) * 2), idesc, acc0 || (pass | ks) != 0);
     }
 }
 template <int KP, bool MN_MAJOR_A>
 __device__ __forceinline__ void issue_ss3_n(int ks, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                            uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+                                            uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool acc0 = false) {
     switch (ks) {
-        case 1: issue_ss3<1, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
-        case 2: issue_ss3<2, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
-        case 3: issue_ss3<3, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
-        case 4: issue_ss3<4, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
-        case 5: if constexpr (KP > 64) issue_ss3<5, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
-        case 6: if constexpr (KP > 64) issue_ss3<6, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
-        case 7: if constexpr (KP > 64) issue_ss3<7, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
-        default: if constexpr (KP > 64) issue_ss3<8, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc); break;
+        case 1: issue_ss3<1, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc, acc0); break;
+        case 2: issue_ss3<2, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc, acc0); break;
+        case 3: issue_ss3<3, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc, acc0); break;
+        case 4: issue_ss3<4, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc, acc0); break;
+        case 5: if constexpr (KP > 64) issue_ss3<5, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc, acc0); break;
+        case 6: if constexpr (KP > 64) issue_ss3<6, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc, acc0); break;
+        case 7: if constexpr (KP > 64) issue_ss3<7, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc, acc0); break;
+        default: if constexpr (KP > 64) issue_ss3<8, KP, MN_MAJOR_A>(d, a_hi, a_lo, b_hi, b_lo, desc_a, desc_b, idesc, acc0); break;
     }
 }
 

@@ -43,7 +43,8 @@ def test_version_and_path_selection(library):
     assert library.dctp_path_for(128, 128, 128) == 1
     assert library.dctp_path_for(32, 16, 16) == 2          # non-square -> CUDA cores
     assert library.dctp_path_for(56, 56, 60) == 2          # strided rows -> CUDA cores
-    assert library.dctp_path_for(320, 320, 320) == 2
+    assert library.dctp_path_for(320, 320, 320) == 4        # tiled tensor-core kernel for large maps
+    assert library.dctp_path_for(130, 130, 130) == 2        # side not a multiple of 16 -> CUDA cores
     assert library.dctp_path_for(56, 56, 56) in (1, 3)
 
 

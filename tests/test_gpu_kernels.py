@@ -102,6 +102,28 @@ def test_general_shapes_on_cuda_cores(lib, cuda_device, shape):
         assert np.abs(co.cpu().numpy() - z).max() / np.abs(z).max() < 2e-5
 
 
+@pytest.mark.parametrize('n', [144, 160, 176, 256, 288, 320])
+def test_large_map_kernel(lib, cuda_device, n):
+    """Tiled tensor-core kernel for U^2-Netp's large stages: energies vs the float64 oracle and vs the CUDA-core
+    kernel, coefficients vs scipy, several maps per channel and more work items than SMs."""
+    from scipy.fft import dctn
+    from dct_pruning_b200.ops import dct_energy
+    x = relu_maps((2, 3, n, n), seed=400 + n, dead_every=3)
+    acc, en, co = dct_energy(x.to(cuda_device), path='large', want_energy=True, want_coeff=True)
+    want = port.energy_scipy64(x.numpy())
+    en = en.cpu().numpy()
+    live = want > 0
+    assert (en[~live] == 0).all()
+    assert rel_err(en[live], want[live]).max() < ENERGY_TOL
+    z = dctn(x.numpy().astype(np.float64), type=2, norm='ortho', axes=(-2, -1))
+    assert np.abs(co.cpu().numpy() - z).max() / np.abs(z).max() < 2e-5
+    assert rel_err(acc.cpu().numpy()[want.sum(0) > 0], want.sum(0)[want.sum(0) > 0]).max() < ENERGY_TOL
+    many = relu_maps((3, 70, n, n), seed=500 + n) if n <= 160 else relu_maps((2, 40, n, n), seed=500 + n)
+    _, en_l, _ = dct_energy(many.to(cuda_device), path='large', want_energy=True)
+    pars = port.energy_parseval64(many.numpy())
+    assert rel_err(en_l.cpu().numpy(), pars).max() < ENERGY_TOL
+
+
 @pytest.mark.parametrize('path', ['umma', 'simt'])
 def test_known_answer_vectors(lib, cuda_device, path):
     from dct_pruning_b200.ops import dct_energy
