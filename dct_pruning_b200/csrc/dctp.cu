@@ -314,7 +314,7 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
     a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
     if (energy_out) CUDA_TRY(cudaMemsetAsync(energy_out, 0, sizeof(float) * a.n_maps, stream));
     int grid = g.sm_count < a.n_items ? g.sm_count : a.n_items;
-    score_large_kernel<<<grid, 128, LargeSmem::TOTAL, stream>>>(a);
+    score_large_kernel<<<grid, LARGE_NT, LargeSmem::TOTAL, stream>>>(a);
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     return DCTP_OK;
