@@ -36,6 +36,8 @@ class ScoreSession:
         self.images = [0] * len(self.sites)
         self.handles = []
         self.lib = _lib.load()
+        self._score_accum = self.lib.dctp_score_accum
+        self._plans = [None] * len(self.sites)
         self.launches = 0
 
     # ------------------------------------------------------------------ registration
@@ -74,21 +76,26 @@ class ScoreSession:
             raise ValueError('site %r: expected an NCHW activation, got shape %s' % (self.sites[idx].module, tuple(t.shape)))
         if t.dtype != torch.float32:
             t = t.float()                     # the reference scores in fp32 (common.py:233,289)
-        if t.stride(3) != 1 or t.stride(2) < t.shape[3]:
-            t = t.contiguous()
+        sb, sc, sh, sw = t.stride()
         B, C, H, W = t.shape
-        if self.sites[idx].variant == VARIANT_LAST12:
-            if C < DENSENET_WINDOW:
-                raise ValueError('site %r: DenseNet window needs >= %d channels, got %d'
-                                 % (self.sites[idx].module, DENSENET_WINDOW, C))
-            c_begin, c_count = C - DENSENET_WINDOW, DENSENET_WINDOW
-        else:
-            c_begin, c_count = 0, C
-        off = self._slot(idx, c_count, t.device)
-        acc = self.flat[off:off + c_count]
-        _lib.check(self.lib.dctp_score_accum(_lib.ptr(t), B, H, W, t.stride(0), t.stride(1), t.stride(2),
-                                             c_begin, c_count, _lib.ptr(acc), None, None,
-                                             self.path, _lib.current_stream()))
+        if sw != 1 or sh < W:
+            t = t.contiguous()
+            sb, sc, sh, sw = t.stride()
+        plan = self._plans[idx]
+        if plan is None or plan[0] != C:      # (channels, c_begin, c_count, accumulator address): fixed after the first firing
+            if self.sites[idx].variant == VARIANT_LAST12:
+                if C < DENSENET_WINDOW:
+                    raise ValueError('site %r: DenseNet window needs >= %d channels, got %d'
+                                     % (self.sites[idx].module, DENSENET_WINDOW, C))
+                c_begin, c_count = C - DENSENET_WINDOW, DENSENET_WINDOW
+            else:
+                c_begin, c_count = 0, C
+            off = self._slot(idx, c_count, t.device)
+            plan = self._plans[idx] = (C, c_begin, c_count, self.flat.data_ptr() + 8 * off)
+        code = self._score_accum(t.data_ptr(), B, H, W, sb, sc, sh, plan[1], plan[2], plan[3], None, None, self.path,
+                                 torch.cuda.current_stream().cuda_stream)
+        if code:
+            _lib.check(code)
         self.images[idx] += B
         self.launches += 1
 
@@ -106,6 +113,40 @@ class ScoreSession:
         elif slot[1] != c_count:
             raise ValueError('site %r changed width: %d -> %d channels' % (self.sites[idx].module, slot[1], c_count))
         return slot[0]
+
+    # ------------------------------------------------------------------ CUDA-graph replay (launch-bound nets)
+    def capture(self, example, warmup=2):
+        """Capture one forward pass with every hook launch in a CUDA graph and return `replay(x)`.
+
+        For the CIFAR-sized nets the scoring pass is launch-bound (tens of hooks over a few-millisecond
+        forward); a graph removes the per-launch host cost of both the forward and the hooks.  `example`
+        fixes shape and device; hooks must be registered (use inside `with session:`).  Each `replay(x)`
+        scores one more batch, exactly like calling `net(x)` with the hooks live."""
+        if not self.handles:
+            raise RuntimeError('register the hooks before capturing (with session: ...)')
+        static_in = example.detach().clone()
+        side = torch.cuda.Stream(device=static_in.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):             # allocates accumulator slots, uploads bases, warms cuDNN
+                self.net(static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(static_in.device)
+        self.reset()
+        before = list(self.images)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.no_grad():
+            self.net(static_in)
+        per_replay = [after - b for after, b in zip(self.images, before)]
+        self.images = before                            # the capture pass itself did not run
+        self._graph = graph                             # keep alive
+
+        def replay(x):
+            static_in.copy_(x, non_blocking=True)
+            graph.replay()
+            for i, n in enumerate(per_replay):
+                self.images[i] += n
+        return replay
 
     def prepare(self, sides):
         """Upload the cosine bases for the given map sides ahead of time (keeps hooks capture-safe)."""

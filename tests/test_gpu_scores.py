@@ -127,3 +127,28 @@ def test_simt_and_umma_paths_agree_end_to_end(lib, cuda_device):
     _, b = generate('googlenet_b2_l1', cuda_device, path='simt')
     for stem in a:
         np.testing.assert_allclose(a[stem], b[stem], rtol=3e-5, atol=0)
+
+
+def test_cuda_graph_replay_matches_eager(lib, cuda_device):
+    """Forward + all hook launches captured in a CUDA graph (launch-bound CIFAR nets) give the eager scores."""
+    from dct_pruning_b200.generate import synthetic_batches
+    from dct_pruning_b200.hooks import ScoreSession
+    from dct_pruning_b200.zoo import get_network
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    net = get_network('resnet_56').to(cuda_device).eval()
+    batches = [x.to(cuda_device) for x, _ in synthetic_batches(16, 32, 3)]
+    eager = ScoreSession(net, 'resnet_56')
+    with eager, torch.no_grad():
+        for x in batches:
+            net(x)
+    want = eager.finalize()
+    graphed = ScoreSession(net, 'resnet_56')
+    with graphed:
+        replay = graphed.capture(batches[0])
+        for x in batches:
+            replay(x)
+    got = graphed.finalize()
+    assert sorted(got) == sorted(want) and graphed.n_images == 48
+    for stem in want:
+        np.testing.assert_allclose(got[stem], want[stem], rtol=1e-6, atol=0)
