@@ -342,6 +342,8 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
     a.num_tiles = (a.n_maps + a.G - 1) / a.G;
     a.K1S = (a.G * N + 15) / 16; a.N1 = (N + 15) / 16 * 16;
     a.TPM = pow2_floor(128 / a.G < 32 ? 128 / a.G : 32);
+    a.tpm_shift = 0;
+    while ((1 << a.tpm_shift) < a.TPM) ++a.tpm_shift;
     a.idesc = umma::make_idesc_bf16(128, a.N1, false, false);
     a.scatter = basis.scatter; a.scatter_bytes = static_cast<uint32_t>(basis.tile_vec) * basis.vpe * 2u;
     a.a_hi = basis.a_hi; a.a_lo = basis.a_lo; a.c_hi = basis.c_hi; a.c_lo = basis.c_lo;
@@ -360,6 +362,7 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
     int grid = g.sm_count;
     const int need = (a.num_tiles + ns - 1) / ns;
     if (grid > need) grid = need;
+    a.chan_step = static_cast<int>((static_cast<long long>(grid) * ns * a.G) % c_count);
     const bool v2 = basis.vpe == 2;
     if (n1max == 64) {
         if (v2) score_t_kernel<64, 3, 2><<<grid, 384, smem, stream>>>(a);
@@ -410,6 +413,8 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
     else { a.NQ = a.J; a.K2S = (a.Ms + 15) / 16; a.N2 = 16 * a.K2S; }
     a.a2_lbo = static_cast<uint32_t>(a.K2S) * 2048u; a.a2_group_bytes = 2u * a.a2_lbo;
     a.TPM = pow2_floor(128 / a.MT < 32 ? 128 / a.MT : 32);
+    a.tpm_shift = 0;
+    while ((1 << a.tpm_shift) < a.TPM) ++a.tpm_shift;
     a.idesc1 = umma::make_idesc_bf16(128, a.N1, false, false);
     a.idesc2 = umma::make_idesc_bf16(128, a.N2, true, false);
     a.basis_hi = basis.hi; a.basis_lo = basis.lo;
@@ -439,6 +444,7 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
     const size_t smem = UmmaScoreSmem<KP>::total(a.red_bytes, a.var_bytes);
     int grid = g.sm_count * umma_occupancy(KP, mode, pf, smem);
     if (grid > a.num_tiles) grid = a.num_tiles;
+    a.chan_step = static_cast<int>((static_cast<long long>(grid) * a.MT) % c_count);
     switch (mode) {
         case LOAD_DENSE1:
             if (pf) score_umma_kernel<KP, LOAD_DENSE1, true><<<grid, 128, smem, stream>>>(a);

@@ -57,7 +57,8 @@ struct TScoreArgs {
     int num_tiles;
     int K1S;                        // stage-1 k-steps = ceil(G*N / 16)
     int N1;                         // N rounded up to 16: MMA N of both stages, contraction length of stage 2
-    int TPM;                        // threads per map in the final reduction
+    int TPM, tpm_shift;             // threads per map in the final reduction (power of two), its log2
+    int chan_step;                  // (tiles between a slot's consecutive tiles * G) mod c_count
     uint32_t idesc;                 // M = 128, N = N1, bf16 x bf16 -> f32, K-major B
     const uint16_t* scatter;        // [tile_vec][VPE] byte offsets of each float4's pieces in the K-major data operand
     uint32_t scatter_bytes;
@@ -223,6 +224,12 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     uint32_t phase = 0;
     bool alive = true;
 
+    // final reduction roles, fixed for the whole kernel
+    const uint32_t tpm = a.TPM;
+    const uint32_t red_t = wtid >> a.tpm_shift, red_sub = wtid & (tpm - 1);
+    const float* red_row = red + min(red_t, (uint32_t)a.G - 1) * a.Ms;
+    uint32_t chan = (uint32_t)((static_cast<long long>(first) * a.G + red_t) % a.c_count);
+
     int trace_i = 0;
     auto stamp = [&](int k) {
         if (a.trace != nullptr && blockIdx.x == 0 && wtid == 0 && wg == 0 && trace_i < 32) a.trace[trace_i * 8 + k] = clock64();
@@ -324,19 +331,18 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
         named_bar_sync(bar_id, TPS);
         {
             // TPM threads per map, fixed summation order -> bit-reproducible per-map energy
-            const uint32_t t = wtid / a.TPM, sub = wtid % a.TPM;
-            const bool live = (int)t < maps_here;
             float s = 0.f;
-            if (live) {
-                const float* rp = red + t * a.Ms;
-                for (uint32_t v = sub; v < (uint32_t)a.N; v += a.TPM) s += rp[v];
+            if (red_sub < (uint32_t)a.N) s = red_row[red_sub];
+            if (red_sub + tpm < (uint32_t)a.N) s += red_row[red_sub + tpm];      // N <= 2 * TPM for every shape routed here
+#pragma unroll
+            for (uint32_t o = 16; o > 0; o >>= 1)
+                if (o < tpm) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((int)red_t < maps_here && red_sub == 0) {
+                atomicAdd(a.accum + chan, (double)s);
+                if (a.energy_out) a.energy_out[map0 + (int)red_t] = s;
             }
-            for (uint32_t o = a.TPM >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (live && sub == 0) {
-                const int mm = map0 + (int)t;
-                atomicAdd(a.accum + (mm % a.c_count), (double)s);
-                if (a.energy_out) a.energy_out[mm] = s;
-            }
+            chan += a.chan_step;                                   // (map0 + red_t) mod c_count, without the division
+            if (chan >= (uint32_t)a.c_count) chan -= a.c_count;
         }
         stamp(7);
         ++trace_i;

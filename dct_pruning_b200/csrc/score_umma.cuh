@@ -67,7 +67,8 @@ struct UmmaScoreArgs {
     int K1;                         // stage-1 k-steps (16 columns each) = ceil(J*Ms / 16)
     int N1;                         // stage-1 output columns = 16*K1
     int NQ, K2S, N2;                // stage-2: groups, k-steps per group, output columns per group
-    int TPM;                        // threads per map in the final reduction (power of two <= 32, TPM*MT <= 128)
+    int TPM, tpm_shift;             // threads per map in the final reduction (power of two <= 32, TPM*MT <= 128), its log2
+    int chan_step;                  // (gridDim.x * MT) mod c_count: channel advance between a CTA's consecutive tiles
     uint32_t idesc1, idesc2;
     uint32_t a2_lbo, a2_group_bytes;
     FastDiv div_vpm, div_n, div_ms, div_j;
@@ -480,6 +481,14 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
             __syncwarp();
         }
     };
+    // final reduction roles, fixed for the whole kernel
+    const uint32_t tpm = a.TPM;
+    const uint32_t red_t = tid >> a.tpm_shift, red_sub = tid & (tpm - 1);
+    const uint32_t red_g = a.div_j.div(min(red_t, (uint32_t)a.MT - 1)), red_j = min(red_t, (uint32_t)a.MT - 1) - red_g * a.J;
+    const uint32_t red_rows = ms8 ? 1u : blocks_per_q;
+    const float* red_row = red + (ms8 ? red_j : red_j * blocks_per_q) * 128 + red_g * a.Ms;
+    uint32_t chan = (uint32_t)((static_cast<long long>(blockIdx.x) * a.MT + red_t) % a.c_count);
+
     auto epilogue2 = [&](int tile) {
         const int map0 = tile * a.MT;
         const int maps_here = min(a.MT, a.n_maps - map0);
@@ -546,24 +555,23 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         __syncthreads();
         {
             // TPM threads per map, fixed summation order -> bit-reproducible per-map energy
-            const uint32_t t = tid / a.TPM, sub = tid % a.TPM;
             float s = 0.f;
-            const bool live = (int)t < maps_here;
+            const bool live = (int)red_t < maps_here;
             if (live) {
-                const uint32_t g = a.div_j.div(t), j = t - g * a.J;
-                const uint32_t rows = ms8 ? 1u : blocks_per_q, first = ms8 ? j : j * blocks_per_q;
-                for (uint32_t row = 0; row < rows; ++row) {
-                    const float* rp = red + (first + row) * 128 + g * a.Ms;
-                    for (uint32_t v = sub; v < (uint32_t)a.N; v += a.TPM) s += rp[v];
+                for (uint32_t row = 0; row < red_rows; ++row) {
+                    const float* rp = red_row + row * 128;
+                    for (uint32_t v = red_sub; v < (uint32_t)a.N; v += tpm) s += rp[v];
                 }
             }
-            for (uint32_t o = a.TPM >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (live && sub == 0) {
-                int mm = map0 + (int)t;
-                int c = mm % a.c_count;
-                atomicAdd(a.accum + c, (double)s);
-                if (a.energy_out) a.energy_out[mm] = s;
+#pragma unroll
+            for (uint32_t o = 16; o > 0; o >>= 1)
+                if (o < tpm) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (live && red_sub == 0) {
+                atomicAdd(a.accum + chan, (double)s);
+                if (a.energy_out) a.energy_out[map0 + (int)red_t] = s;
             }
+            chan += a.chan_step;                                   // (map0 + red_t) mod c_count, without the division
+            if (chan >= (uint32_t)a.c_count) chan -= a.c_count;
         }
     };
 
