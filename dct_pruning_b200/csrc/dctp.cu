@@ -48,7 +48,7 @@ struct TBasis {                                                          // per 
     uint16_t* scatter = nullptr;                                         // [tile_vec][vpe]
     int tile_vec = 0, vpe = 1;
 };
-struct LargeBasis { uint16_t *hi = nullptr, *lo = nullptr; int NP = 0; };   // [NP][NP] C_N zero padded, NP = N rounded up to 64
+struct LargeBasis { uint16_t *hi = nullptr, *lo = nullptr; int NP = 0, NPR = 0; };   // operand image of C_N: [NP/64][NPR][64], see get_large_basis
 struct SimtBasis { float* t = nullptr; };                               // [N x N], t[n*N + k] = C_N[k][n]
 
 struct State {
@@ -63,6 +63,7 @@ struct State {
     std::map<int, LargeBasis> large;                   // N
     int t_slots = 3;                                   // tile slots per CTA of the TMEM-operand kernel (DCTP_T_SLOTS=0 disables it)
     bool t_all = false;
+    bool pdl = true;                                   // programmatic dependent launch of the score kernels (DCTP_PDL=0 disables)
     int t_auto_lo = 52;                                // smallest side AUTO routes to the TMEM-operand kernel (DCTP_T_LO)
     int regs[2][6][2] = {};                            // registers/thread per (KP, load mode, prefetch) instantiation
     // scratch of dctp_score_host (grow-only)
@@ -172,14 +173,28 @@ int get_t_basis(int N, TBasis& out) {
     return DCTP_OK;
 }
 
+// stage-2 output chunks of the large-map kernel: NUC chunks of NU columns (multiple of 16, at most 128: one basis slab)
+void large_u_chunks(int N, int& nu, int& nuc) {
+    nuc = (N + 127) / 128;
+    nu = ((N + nuc - 1) / nuc + 15) / 16 * 16;
+}
+
 int get_large_basis(int N, LargeBasis& out) {
     auto it = g.large.find(N);
     if (it != g.large.end()) { out = it->second; return DCTP_OK; }
     LargeBasis b;
     b.NP = (N + 63) / 64 * 64;
-    std::vector<uint16_t> hi(static_cast<size_t>(b.NP) * b.NP, 0), lo(hi.size(), 0);
+    // operand image: [column block cb][row k][64 columns], the eight 16-byte chunks of a row XOR-swizzled by (k & 7);
+    // rows padded so that every u-chunk slab of the kernel stays inside its column block
+    int nu, nuc;
+    large_u_chunks(N, nu, nuc);
+    b.NPR = b.NP > nu * nuc ? b.NP : nu * nuc;
+    std::vector<uint16_t> hi(static_cast<size_t>(b.NP / 64) * b.NPR * 64, 0), lo(hi.size(), 0);
     for (int k = 0; k < N; ++k)
-        for (int n = 0; n < N; ++n) split_bf16(dct_coef(k, n, N), hi[(size_t)k * b.NP + n], lo[(size_t)k * b.NP + n]);
+        for (int n = 0; n < N; ++n) {
+            const size_t at = (static_cast<size_t>(n >> 6) * b.NPR + k) * 64 + ((((n & 63) >> 3) ^ (k & 7)) << 3) + (n & 7);
+            split_bf16(dct_coef(k, n, N), hi[at], lo[at]);
+        }
     CUDA_TRY(cudaMalloc(&b.hi, hi.size() * 2));
     CUDA_TRY(cudaMalloc(&b.lo, lo.size() * 2));
     CUDA_TRY(cudaMemcpy(b.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
@@ -201,6 +216,24 @@ int get_simt_basis(int N, SimtBasis& out) {
     g.simt[N] = b;
     out = b;
     return DCTP_OK;
+}
+
+// Score kernels are launched with programmatic stream serialization: their prologue (shared-memory fill, basis staging,
+// TMEM allocation) may run while the preceding kernel drains; each kernel waits for that kernel's completion
+// (griddepcontrol.wait) before it touches the activation.  DCTP_PDL=0 turns it off.
+template <typename Args>
+cudaError_t launch_score(void (*kern)(const Args), int grid, int block, size_t smem, cudaStream_t stream, const Args& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(block));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args);
 }
 
 // ------------------------------------------------------------------ init
@@ -267,6 +300,7 @@ int ensure_init() {
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
     }
+    if (const char* e = std::getenv("DCTP_PDL")) g.pdl = std::atoi(e) != 0;
     if (const char* e = std::getenv("DCTP_T_SLOTS")) g.t_slots = std::atoi(e);
     if (g.t_slots != 0) g.t_slots = 3;
     CUDA_TRY(cudaFuncSetAttribute(score_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LargeSmem::TOTAL));
@@ -307,14 +341,29 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
     LargeScoreArgs a;
     std::memset(&a, 0, sizeof a);
     a.x_dense = first; a.n_maps = B * c_count; a.c_count = c_count;
-    a.N = N; a.NP = basis.NP; a.NVC = (N + 127) / 128;
-    a.NU = N <= 160 ? N : ((N / 2 + 15) / 16) * 16; a.NUC = N <= 160 ? 1 : 2;
+    a.N = N; a.NPR = basis.NPR; a.NVC = (N + 127) / 128;
+    large_u_chunks(N, a.NU, a.NUC);
     a.n_items = a.n_maps * a.NVC;
-    a.c_hi = basis.hi; a.c_lo = basis.lo;
+    a.c_hi = reinterpret_cast<const uint8_t*>(basis.hi); a.c_lo = reinterpret_cast<const uint8_t*>(basis.lo);
     a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
     if (energy_out) CUDA_TRY(cudaMemsetAsync(energy_out, 0, sizeof(float) * a.n_maps, stream));
     int grid = g.sm_count < a.n_items ? g.sm_count : a.n_items;
-    score_large_kernel<<<grid, LARGE_NT, LargeSmem::TOTAL, stream>>>(a);
+    if (const char* e = std::getenv("DCTP_L_EXP")) a.exp_flags = std::atoi(e);
+    static long long* trace_buf = nullptr;
+    const bool tracing = std::getenv("DCTP_L_TRACE") != nullptr;
+    if (tracing) {
+        if (!trace_buf) CUDA_TRY(cudaMalloc(&trace_buf, 12 * sizeof(long long)));
+        a.trace = trace_buf;
+    }
+    CUDA_TRY(launch_score(score_large_kernel, grid, LARGE_NT, LargeSmem::TOTAL, stream, a));
+    if (tracing) {
+        long long h[12];
+        CUDA_TRY(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
+        const double n = h[7] > 0 ? double(h[7]) : 1.0;
+        fprintf(stderr, "[dctp trace] large N=%d steps=%lld, issuer thread cycles/step: total %.0f | waiting for: map slab %.0f, "
+                        "basis slab %.0f (+%.0f look-ahead), A2 %.0f, D2 free %.0f\n",
+                N, h[7], h[6] / n, h[1] / n, h[4] / n, h[5] / n, h[2] / n, h[3] / n);
+    }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     return DCTP_OK;
@@ -365,14 +414,14 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
     a.chan_step = static_cast<int>((static_cast<long long>(grid) * ns * a.G) % c_count);
     const bool v2 = basis.vpe == 2;
     if (n1max == 64) {
-        if (v2) score_t_kernel<64, 3, 2><<<grid, 384, smem, stream>>>(a);
-        else score_t_kernel<64, 3, 1><<<grid, 384, smem, stream>>>(a);
+        if (v2) CUDA_TRY(launch_score(score_t_kernel<64, 3, 2>, grid, 384, smem, stream, a));
+        else CUDA_TRY(launch_score(score_t_kernel<64, 3, 1>, grid, 384, smem, stream, a));
     } else if (n1max == 32) {
-        if (v2) score_t_kernel<32, 6, 2><<<grid, 768, smem, stream>>>(a);
-        else score_t_kernel<32, 6, 1><<<grid, 768, smem, stream>>>(a);
+        if (v2) CUDA_TRY(launch_score(score_t_kernel<32, 6, 2>, grid, 768, smem, stream, a));
+        else CUDA_TRY(launch_score(score_t_kernel<32, 6, 1>, grid, 768, smem, stream, a));
     } else {
-        if (v2) score_t_kernel<16, 6, 2><<<grid, 768, smem, stream>>>(a);
-        else score_t_kernel<16, 6, 1><<<grid, 768, smem, stream>>>(a);
+        if (v2) CUDA_TRY(launch_score(score_t_kernel<16, 6, 2>, grid, 768, smem, stream, a));
+        else CUDA_TRY(launch_score(score_t_kernel<16, 6, 1>, grid, 768, smem, stream, a));
     }
     if (tracing) {
         long long h[256];
@@ -447,20 +496,20 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
     a.chan_step = static_cast<int>((static_cast<long long>(grid) * a.MT) % c_count);
     switch (mode) {
         case LOAD_DENSE1:
-            if (pf) score_umma_kernel<KP, LOAD_DENSE1, true><<<grid, 128, smem, stream>>>(a);
-            else score_umma_kernel<KP, LOAD_DENSE1, false><<<grid, 128, smem, stream>>>(a);
+            if (pf) CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_DENSE1, true>, grid, 128, smem, stream, a));
+            else CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_DENSE1, false>, grid, 128, smem, stream, a));
             break;
         case LOAD_DENSE2:
-            if (pf) score_umma_kernel<KP, LOAD_DENSE2, true><<<grid, 128, smem, stream>>>(a);
-            else score_umma_kernel<KP, LOAD_DENSE2, false><<<grid, 128, smem, stream>>>(a);
+            if (pf) CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_DENSE2, true>, grid, 128, smem, stream, a));
+            else CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_DENSE2, false>, grid, 128, smem, stream, a));
             break;
         case LOAD_DENSE4:
-            if (pf) score_umma_kernel<KP, LOAD_DENSE4, true><<<grid, 128, smem, stream>>>(a);
-            else score_umma_kernel<KP, LOAD_DENSE4, false><<<grid, 128, smem, stream>>>(a);
+            if (pf) CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_DENSE4, true>, grid, 128, smem, stream, a));
+            else CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_DENSE4, false>, grid, 128, smem, stream, a));
             break;
-        case LOAD_GEN4: score_umma_kernel<KP, LOAD_GEN4, false><<<grid, 128, smem, stream>>>(a); break;
-        case LOAD_GEN2: score_umma_kernel<KP, LOAD_GEN2, false><<<grid, 128, smem, stream>>>(a); break;
-        default: score_umma_kernel<KP, LOAD_GEN1, false><<<grid, 128, smem, stream>>>(a); break;
+        case LOAD_GEN4: CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_GEN4, false>, grid, 128, smem, stream, a)); break;
+        case LOAD_GEN2: CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_GEN2, false>, grid, 128, smem, stream, a)); break;
+        default: CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_GEN1, false>, grid, 128, smem, stream, a)); break;
     }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());

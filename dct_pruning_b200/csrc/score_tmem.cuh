@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     // tiles of this slot: tile = first + i * stride
     const int first = blockIdx.x * NSLOT + (int)wg, stride = gridDim.x * NSLOT;
 
-    // ---- the first tile's loads go out before anything else
+    // ---- register prefetch of a tile
     float4 pf[TSCORE_PF];
     uint32_t pf_full = 0;
     auto prefetch = [&](int tile) {
@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
         for (int u = 0; u < TSCORE_PF; ++u)
             if (wtid + u * TPS < pf_full) pf[u] = detail::ldg_stream(src + u * TPS);
     };
-    if (first < a.num_tiles) prefetch(first);
+    launch_dependents();
 
-    // ---- one-time setup: zero the data operands, stage C and the scatter table, barriers, TMEM, A' into TMEM
+    // ---- one-time setup (independent of the activation: overlaps the preceding kernel's tail under a dependent launch): zero the data operands, stage C and the scatter table, barriers, TMEM, A' into TMEM
     for (uint32_t off = tid * 16; off < S::off_c(NSLOT); off += NT * 16)
         *reinterpret_cast<uint4*>(smem + off) = make_uint4(0, 0, 0, 0);
     for (uint32_t i = tid; i < 64 * 8; i += NT) {
@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+
+    grid_dependency_wait();                                        // the activation (written by the preceding kernel) is complete
+    if (first < a.num_tiles) prefetch(first);
 
     const uint32_t slot_col = tmem + 128 + SLOT_COLS * wg;         // this slot's TMEM columns
     const uint32_t d_col = slot_col, a2_hi_col = slot_col + N1MAX, a2_lo_col = slot_col + N1MAX + N1MAX / 2;

@@ -215,6 +215,26 @@ __device__ __forceinline__ void issue_ss3_n(int ks, uint32_t d, uint32_t a_hi, u
     }
 }
 
+// one pass (one hi/lo operand pair) of a <= 64-deep product: ks k-steps, straight-line for each count
+template <int KS, bool MN_MAJOR_A>
+__device__ __forceinline__ void issue_ss_pass(uint32_t d, uint32_t la, uint32_t lb, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              bool acc_first) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+        umma::mma_bf16_ss(d, umma::desc_with_lo(desc_a, la + (MN_MAJOR_A ? ks * 128 : ks * 2)), umma::desc_with_lo(desc_b, lb + ks * 2), idesc,
+                          acc_first || ks != 0);
+}
+template <bool MN_MAJOR_A>
+__device__ __forceinline__ void issue_ss_pass_n(int ks, uint32_t d, uint32_t la, uint32_t lb, uint64_t desc_a, uint64_t desc_b,
+                                                uint32_t idesc, bool acc_first) {
+    switch (ks) {
+        case 1: issue_ss_pass<1, MN_MAJOR_A>(d, la, lb, desc_a, desc_b, idesc, acc_first); break;
+        case 2: issue_ss_pass<2, MN_MAJOR_A>(d, la, lb, desc_a, desc_b, idesc, acc_first); break;
+        case 3: issue_ss_pass<3, MN_MAJOR_A>(d, la, lb, desc_a, desc_b, idesc, acc_first); break;
+        default: issue_ss_pass<4, MN_MAJOR_A>(d, la, lb, desc_a, desc_b, idesc, acc_first); break;
+    }
+}
+
 }  // namespace detail
 
 template <int KP>
@@ -267,7 +287,7 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         return;
     }
 
-    // ---- prefetch of the first tile goes out before anything else
+    // ---- register prefetch of a tile's stream
     [[maybe_unused]] float4 pf[SLOTS];
     [[maybe_unused]] uint32_t pf_full = 0;
     auto tile_vectors = [&](int tile) -> uint32_t {                // whole float4 vectors of this tile's stream
@@ -281,11 +301,9 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         for (int u = 0; u < SLOTS; ++u)
             if (tid + u * 128 < pf_full) pf[u] = detail::ldg_stream(src + u * 128);
     };
-    if constexpr (PF) {
-        if ((int)blockIdx.x < a.num_tiles) prefetch(blockIdx.x);
-    }
-
-    // ---- one-time setup: zero the operand area, stage basis and scatter table, TMEM, barrier
+    // ---- one-time setup: zero the operand area, stage basis and scatter table, TMEM, barrier.  None of it touches
+    //      the activation, so under a programmatic dependent launch it overlaps the tail of the preceding kernel.
+    launch_dependents();
     for (uint32_t off = tid * 16; off < S::OFF_B_HI; off += 128 * 16)
         *reinterpret_cast<uint4*>(smem + off) = make_uint4(0, 0, 0, 0);
     for (uint32_t i = tid; i < KP * (KP / 8); i += 128) {
@@ -575,6 +593,10 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         }
     };
 
+    grid_dependency_wait();                                        // the activation (written by the preceding kernel) is complete
+    if constexpr (PF) {
+        if ((int)blockIdx.x < a.num_tiles) prefetch(blockIdx.x);
+    }
     int tile = blockIdx.x;
     if (tile < a.num_tiles) stage0(tile);
     while (tile < a.num_tiles) {

@@ -73,6 +73,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// Programmatic dependent launch: `launch_dependents` lets the next kernel of the stream (if it was launched with the
+// programmatic-serialization attribute) start its prologue while this grid is still running; `grid_dependency_wait`
+// blocks until the preceding grid has completed and its memory is visible.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void grid_dependency_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
