@@ -348,21 +348,23 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
     a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
     if (energy_out) CUDA_TRY(cudaMemsetAsync(energy_out, 0, sizeof(float) * a.n_maps, stream));
     int grid = g.sm_count < a.n_items ? g.sm_count : a.n_items;
-    if (const char* e = std::getenv("DCTP_L_EXP")) a.exp_flags = std::atoi(e);
     static long long* trace_buf = nullptr;
     const bool tracing = std::getenv("DCTP_L_TRACE") != nullptr;
     if (tracing) {
-        if (!trace_buf) CUDA_TRY(cudaMalloc(&trace_buf, 12 * sizeof(long long)));
+        if (!trace_buf) CUDA_TRY(cudaMalloc(&trace_buf, 16 * sizeof(long long)));
         a.trace = trace_buf;
     }
     CUDA_TRY(launch_score(score_large_kernel, grid, LARGE_NT, LargeSmem::TOTAL, stream, a));
     if (tracing) {
-        long long h[12];
+        long long h[16];
         CUDA_TRY(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
         const double n = h[7] > 0 ? double(h[7]) : 1.0;
         fprintf(stderr, "[dctp trace] large N=%d steps=%lld, issuer thread cycles/step: total %.0f | waiting for: map slab %.0f, "
                         "basis slab %.0f (+%.0f look-ahead), A2 %.0f, D2 free %.0f\n",
                 N, h[7], h[6] / n, h[1] / n, h[4] / n, h[5] / n, h[2] / n, h[3] / n);
+        const double m = h[12] > 0 ? double(h[12]) : 1.0;
+        fprintf(stderr, "[dctp trace] converter thread 0, cycles per map slab (%lld slabs): buffer wait %.0f, convert+store %.0f, "
+                        "fence+arrive %.0f, load issue %.0f\n", h[12], h[8] / m, h[9] / m, h[10] / m, h[11] / m);
     }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());

@@ -135,8 +135,6 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
         for (int u = 0; u < TSCORE_PF; ++u)
             if (wtid + u * TPS < pf_full) pf[u] = detail::ldg_stream(src + u * TPS);
     };
-    launch_dependents();
-
     // ---- one-time setup (independent of the activation: overlaps the preceding kernel's tail under a dependent launch): zero the data operands, stage C and the scatter table, barriers, TMEM, A' into TMEM
     for (uint32_t off = tid * 16; off < S::off_c(NSLOT); off += NT * 16)
         *reinterpret_cast<uint4*>(smem + off) = make_uint4(0, 0, 0, 0);
@@ -180,6 +178,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     __syncthreads();
     tc_fence_after_sync();
 
+    launch_dependents();                                           // only now: this CTA holds its TMEM columns (see score_umma.cuh)
     grid_dependency_wait();                                        // the activation (written by the preceding kernel) is complete
     if (first < a.num_tiles) prefetch(first);
 

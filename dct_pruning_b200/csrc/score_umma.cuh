@@ -235,6 +235,23 @@ __device__ __forceinline__ void issue_ss_pass_n(int ks, uint32_t d, uint32_t la,
     }
 }
 
+// one pass of a <= 64-deep product with the A operand in TMEM (packed bf16 pairs, 8 columns per k-step)
+template <int KS>
+__device__ __forceinline__ void issue_ts_pass(uint32_t d, uint32_t a_col, uint32_t lb, uint64_t desc_b, uint32_t idesc, bool acc_first) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+        umma::mma_bf16_ts(d, a_col + 8 * ks, umma::desc_with_lo(desc_b, lb + ks * 2), idesc, acc_first || ks != 0);
+}
+__device__ __forceinline__ void issue_ts_pass_n(int ks, uint32_t d, uint32_t a_col, uint32_t lb, uint64_t desc_b, uint32_t idesc,
+                                                bool acc_first) {
+    switch (ks) {
+        case 1: issue_ts_pass<1>(d, a_col, lb, desc_b, idesc, acc_first); break;
+        case 2: issue_ts_pass<2>(d, a_col, lb, desc_b, idesc, acc_first); break;
+        case 3: issue_ts_pass<3>(d, a_col, lb, desc_b, idesc, acc_first); break;
+        default: issue_ts_pass<4>(d, a_col, lb, desc_b, idesc, acc_first); break;
+    }
+}
+
 }  // namespace detail
 
 template <int KP>
@@ -303,7 +320,6 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
     };
     // ---- one-time setup: zero the operand area, stage basis and scatter table, TMEM, barrier.  None of it touches
     //      the activation, so under a programmatic dependent launch it overlaps the tail of the preceding kernel.
-    launch_dependents();
     for (uint32_t off = tid * 16; off < S::OFF_B_HI; off += 128 * 16)
         *reinterpret_cast<uint4*>(smem + off) = make_uint4(0, 0, 0, 0);
     for (uint32_t i = tid; i < KP * (KP / 8); i += 128) {
@@ -593,6 +609,9 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         }
     };
 
+    // Dependents may start only now that this CTA holds its TMEM columns: a later kernel's CTA that grabbed TMEM first
+    // and then waited for this grid to finish would deadlock against a CTA of this grid still waiting for columns.
+    launch_dependents();
     grid_dependency_wait();                                        // the activation (written by the preceding kernel) is complete
     if constexpr (PF) {
         if ((int)blockIdx.x < a.num_tiles) prefetch(blockIdx.x);

@@ -83,6 +83,17 @@ __device__ __forceinline__ void grid_dependency_wait() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only), grouped; the issuing thread sees the data after the wait
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_but_one() {          // all groups but the most recent one have completed
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
