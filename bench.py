@@ -251,12 +251,12 @@ def run_ours(args):
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     step_graph = None
     if args.graph:                                # launch-bound nets: one CUDA graph per step takes the host out of the loop
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        warm_stream = torch.cuda.Stream(device=device)
+        warm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm_stream):
             for idx, a in enumerate(acts):
                 session.score(idx, a)
-        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream().wait_stream(warm_stream)
         torch.cuda.synchronize()
         step_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(step_graph):
