@@ -393,7 +393,9 @@ def run_ours(args):
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
                          'traffic': traffic, 'peak_kind': peak_kind, 'kernel': dom_name,
                          'share_of_step': dom_ms / sum(per_site_ms),
-                         'launches_per_step': len(dom), 'bytes_per_step': dom_bytes, 'ms_per_step': dom_ms},
+                         'launches_per_step': len(dom), 'bytes_per_step': dom_bytes, 'ms_per_step': dom_ms,
+                         'timing': 'CUDA event pair around every launch, over a repeat of the K timed steps on the same stream '
+                                   '(the events keep consecutive launches from overlapping: isolated launch durations)'},
             'hook_path_GBps': alg_bytes_step * args.steps / (ms_total / 1e3) / 1e9,
             'by_kernel': {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in by_kernel.items()},
             'by_shape': shape_table,
