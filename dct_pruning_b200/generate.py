@@ -48,12 +48,53 @@ def rank_slice(n, rank, world):
     return lo, hi
 
 
+def device_batches(host_batches, device):
+    """Yield device copies of host image batches one step ahead of their use: the H2D copy of batch k+1 runs on a
+    side stream (from pinned memory) under the forward pass of batch k.  Two device buffers are reused in turn; a
+    yielded tensor is valid until the next one is requested."""
+    main = torch.cuda.current_stream(device)
+    copy_stream = torch.cuda.Stream(device=device)
+    bufs, consumed = [None, None], [None, None]
+
+    def put(x, slot):
+        x = x if x.is_pinned() else x.pin_memory()
+        if bufs[slot] is None or bufs[slot].shape != x.shape or bufs[slot].dtype != x.dtype:
+            bufs[slot] = torch.empty(x.shape, dtype=x.dtype, device=device)
+            consumed[slot] = None
+        with torch.cuda.stream(copy_stream):
+            if consumed[slot] is not None:
+                copy_stream.wait_event(consumed[slot])      # the forward pass that read this buffer has finished
+            bufs[slot].copy_(x, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        return x, slot, done                                # (the pinned source stays referenced until its copy is consumed)
+
+    def take(pending):
+        _, slot, done = pending
+        main.wait_event(done)
+        return slot
+
+    pending, k = None, 0
+    for x in host_batches:
+        ahead = put(x, k & 1)
+        k += 1
+        if pending is not None:
+            slot = take(pending)
+            yield bufs[slot]
+            consumed[slot] = torch.cuda.Event()
+            consumed[slot].record(main)
+        pending = ahead
+    if pending is not None:
+        slot = take(pending)
+        yield bufs[slot]
+
+
 def inference(net, loader, limit, device, rank=0, world=1):
     """eval + no_grad forward over the first `limit` batches (common.py:312-320); under
     world > 1 each rank forwards its contiguous slice of every batch."""
     net.eval()
-    n = 0
-    with torch.no_grad():
+
+    def shards():
         for batch_idx, sample in enumerate(loader):
             if batch_idx >= limit:
                 break
@@ -61,10 +102,19 @@ def inference(net, loader, limit, device, rank=0, world=1):
             if world > 1:
                 lo, hi = rank_slice(x.shape[0], rank, world)
                 x = x[lo:hi]
-            if x.shape[0] == 0:
-                continue
-            n += x.shape[0]
-            net(x.to(device, non_blocking=True))
+            if x.shape[0] > 0:
+                yield x
+
+    n = 0
+    with torch.no_grad():
+        if torch.device(device).type == 'cuda':
+            for x in device_batches(shards(), device):
+                n += x.shape[0]
+                net(x)
+        else:                                   # (a CPU net only gets here in tests of the host logic; hooks raise on CPU tensors)
+            for x in shards():
+                n += x.shape[0]
+                net(x.to(device))
     return n
 
 
