@@ -383,6 +383,9 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_hooks_baseline([a[:4].cpu() for a in acts], session.sites, budget_s=12.0)
+        on_gpu = gpu_tensor_reference_baseline(acts, session.sites, budget_s=4.0)
+        if on_gpu is not None:
+            cpu['reference_hook_on_gpu_tensors'] = on_gpu
 
     if rank == 0:
         line = {
@@ -436,6 +439,31 @@ def cpu_hooks_baseline(acts_cpu, sites, budget_s):
             'sample': '%d image(s) x all %d hook sites (%d slices) through oracle.reference_port hooks, hooks only (no CNN forward), %.1f s'
                       % (done, len(sites), slices, dt),
             'us_per_slice': dt / slices * 1e6}
+
+
+def gpu_tensor_reference_baseline(acts, sites, budget_s):
+    """The reference hook in the mode its authors ran it: activations stay on the GPU, one cuFFT-based DCT and one
+    `.item()` sync per (image, channel) slice (oracle port of utils/common.py:262-277).  One image, as many sites as fit."""
+    from oracle import reference_port as port
+    done_sites, slices, t0 = 0, 0, time.perf_counter()
+    total_slices = sum(12 if s.variant == 'D' else a.shape[1] for a, s in zip(acts, sites))
+    for a, site in zip(acts, sites):
+        if site.variant != 'O':
+            continue                               # the other two variants copy every slice to the host for cv2
+        x = a[0:1]
+        port.hook_output(port.ScoreState())(None, (x,), x)
+        torch.cuda.synchronize()
+        slices += x.shape[1]
+        done_sites += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    if slices == 0:
+        return None
+    us = dt / slices * 1e6
+    return {'us_per_slice': us, 'images_per_s_extrapolated': 1e6 / (us * total_slices),
+            'sample': '1 image x %d output-hook site(s) (%d slices) on GPU tensors, per-slice torch.fft DCT + .item() sync, %.1f s; '
+                      'extrapolated linearly to all %d slices of an image' % (done_sites, slices, dt, total_slices)}
 
 
 def run_reference(args):

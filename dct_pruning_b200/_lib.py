@@ -28,6 +28,8 @@ _SIGNATURES = {
     'dctp_finalize': (_c.c_int, [_c.c_void_p, _c.c_double, _c.c_void_p, _c.c_int, _c.c_void_p]),
     'dctp_topk_segmented': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                        _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'dctp_gather_weight': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int,
+                                      _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
     'dctp_check': (_c.c_int, [_c.c_void_p]),
     'dctp_score_host': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                    _c.c_void_p, _c.c_int]),

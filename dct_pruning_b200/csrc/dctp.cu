@@ -16,6 +16,7 @@
 #include "score_tmem.cuh"
 #include "score_umma.cuh"
 #include "topk.cuh"
+#include "gather.cuh"
 
 namespace {
 
@@ -700,6 +701,33 @@ int dctp_topk_segmented(const float* scores, const int* seg_offsets, const int* 
     return DCTP_OK;
 }
 
+int dctp_gather_weight(const float* w, int c_out, int c_in, int inner, const long long* sel_out, int k_out,
+                       const long long* sel_in, int k_in, float* out, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (c_out < 0 || c_in < 0 || inner < 0 || k_out < 0 || k_in < 0)
+        return fail(DCTP_E_INVALID, "dctp_gather_weight: negative size (c_out=%d c_in=%d inner=%d k_out=%d k_in=%d)", c_out, c_in,
+                    inner, k_out, k_in);
+    if ((!sel_out && k_out != c_out) || (!sel_in && k_in != c_in))
+        return fail(DCTP_E_INVALID, "dctp_gather_weight: a NULL selection means all channels (k_out=%d c_out=%d k_in=%d c_in=%d)",
+                    k_out, c_out, k_in, c_in);
+    GatherArgs a;
+    a.w = w; a.out = out; a.sel_out = sel_out; a.sel_in = sel_in;
+    a.c_out = c_out; a.c_in = c_in; a.inner = inner; a.k_out = k_out; a.k_in = k_in;
+    a.total = static_cast<long long>(k_out) * k_in * inner;
+    a.status = g.status;
+    if (a.total == 0) return DCTP_OK;
+    if (!w || !out) return fail(DCTP_E_INVALID, "dctp_gather_weight: null pointer");
+    long long blocks = (a.total + GATHER_THREADS - 1) / GATHER_THREADS;
+    const long long cap = static_cast<long long>(g.sm_count) * 16;
+    if (blocks > cap) blocks = cap;
+    gather_weight_kernel<<<static_cast<unsigned>(blocks), GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    return DCTP_OK;
+}
+
 int dctp_check(void* stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     int rc = ensure_init();
@@ -709,7 +737,8 @@ int dctp_check(void* stream) {
     CUDA_TRY(cudaMemcpy(&st, g.status, sizeof st, cudaMemcpyDeviceToHost));
     if (st != 0) {
         cudaMemset(g.status, 0, sizeof(int));
-        return fail(DCTP_E_DEVICE, "device status %d: a tensor-core completion wait timed out", st);
+        return fail(DCTP_E_DEVICE, st == DCTP_DEV_BAD_INDEX ? "device status %d: a channel index passed to dctp_gather_weight is out of range"
+                                                            : "device status %d: a tensor-core completion wait timed out", st);
     }
     return DCTP_OK;
 }

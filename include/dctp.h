@@ -83,6 +83,15 @@ int dctp_finalize(const double* accum, double n_images, float* out, int n, void*
 int dctp_topk_segmented(const float* scores, const int* seg_offsets, const int* seg_k, int n_seg,
                         long long* out_idx, const int* out_offsets, void* stream);
 
+/* Pruned-weight gather (the step downstream of top-k):
+ *   out[i][j][r] = w[sel_out ? sel_out[i] : i][sel_in ? sel_in[j] : j][r],  i < k_out, j < k_in, r < inner
+ * w is [c_out][c_in][inner] fp32 contiguous (inner = kH*kW; 1 with c_in = 1 for BatchNorm / bias vectors), out is
+ * [k_out][k_in][inner]; sel_out / sel_in are device int64 arrays or NULL for "all, in order" (then k == c).
+ * Replaces the element-wise Python copy loops of utils/load_models.py:43-51, :106-114, :482-500, :526-542,
+ * :633-639 ...  An index outside [0, c) sets the device status word (reported by dctp_check). */
+int dctp_gather_weight(const float* w, int c_out, int c_in, int inner, const long long* sel_out, int k_out,
+                       const long long* sel_in, int k_in, float* out, void* stream);
+
 /* Synchronise `stream` and report the device status word (DCTP_OK or DCTP_E_DEVICE); clears it. */
 int dctp_check(void* stream);
 

@@ -4,7 +4,7 @@ Runs only in the build container (needs /root/reference); the fixtures it writes
 travel with the repo, this script is committed so they can be regenerated:
 
     python tests/golden/make_golden.py            # all fixtures
-    python tests/golden/make_golden.py sites      # one family: sites|scores|topk|shipped
+    python tests/golden/make_golden.py sites      # one family: sites|scores|topk|transfer|shipped
 
 The reference is imported UNMODIFIED.  Its optional imports that are absent from
 this image and never touched on the scoring path are stubbed as empty modules
@@ -281,6 +281,60 @@ def gen_topk(common, load_models):
         print('topk', net_name, len(calls), 'selections')
 
 
+# ---------------------------------------------------------------------- transfer
+def tensor_digests(state_dict):
+    out = {}
+    for k, v in state_dict.items():
+        a = v.detach().cpu().contiguous().numpy()
+        out[k] = [list(a.shape), str(a.dtype), hashlib.sha256(a.tobytes()).hexdigest()]
+    return out
+
+
+def gen_transfer(common, load_models, only=None):
+    """Pruned-weight transfer: run the reference loaders unmodified and record a digest of every tensor of
+    the pruned model they produce (orig net: seed 0, rate 0; pruned net: seed 0, README rate; scores: scores_<tag>.npz)."""
+    for net_name, score_tag, rate_str in TOPK_CASES:
+        if only and only != net_name:
+            continue
+        rate = common.get_compress_rate(types.SimpleNamespace(compress_rate=rate_str))
+        orig = build_net(common, net_name)
+        pruned = build_net(common, net_name, rate)
+        before = tensor_digests(pruned.state_dict())
+        scores = np.load(os.path.join(HERE, 'scores_%s.npz' % score_tag))
+        with tempfile.TemporaryDirectory() as tmp:
+            for k in scores.files:
+                if k != '__meta__':
+                    np.save(os.path.join(tmp, k + '.npy'), scores[k])
+            args = types.SimpleNamespace(imp_score=tmp, net=net_name)
+            od = orig.state_dict()
+            if net_name == 'vgg_16_bn':
+                load_models.load_vgg_model(pruned, od, args)
+            elif net_name == 'resnet_56':
+                load_models.load_resnet_model(pruned, od, 56, args)
+            elif net_name == 'resnet_110':
+                load_models.load_resnet_model(pruned, od, 110, args)
+            elif net_name == 'densenet_40':
+                load_models.load_densenet_model(pruned, od, args)
+            elif net_name == 'googlenet':
+                load_models.load_google_model(pruned, od, args)
+            elif net_name == 'resnet_50':
+                load_models.load_resnet_imagenet_model(pruned, od, args)
+            elif net_name == 'u2netp':
+                load_models.load_u2netp_model(pruned, od, args)
+        after = tensor_digests(pruned.state_dict())
+        # kept small: one digest of the pruned model before the loader, per-tensor digests only where the loader wrote
+        h = hashlib.sha256()
+        for k in before:
+            h.update(k.encode())
+            h.update(before[k][2].encode())
+        changed = {k: after[k] for k in after if after[k][2] != before[k][2]}
+        same = hashlib.sha256(''.join(k + after[k][2] for k in after if after[k][2] == before[k][2]).encode()).hexdigest()
+        with open(os.path.join(HERE, 'transfer_%s.json' % net_name), 'w') as f:
+            json.dump({'net': net_name, 'scores': score_tag, 'compress_rate': rate_str, 'pruned_init_digest': h.hexdigest(),
+                       'n_tensors': len(after), 'changed': changed, 'unchanged_digest': same}, f)
+        print('transfer', net_name, len(after), 'tensors,', len(changed), 'changed by the loader')
+
+
 # ----------------------------------------------------------------------- shipped
 def gen_shipped():
     out = {}
@@ -309,5 +363,7 @@ if __name__ == '__main__':
         gen_scores(common, only)
     if what in ('all', 'topk'):
         gen_topk(common, load_models)
+    if what in ('all', 'transfer'):
+        gen_transfer(common, load_models, only)
     if what in ('all', 'shipped'):
         gen_shipped()
