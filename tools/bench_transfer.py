@@ -14,7 +14,9 @@ from dct_pruning_b200.topk import kept_channels                          # noqa:
 from dct_pruning_b200.zoo import get_network                             # noqa: E402
 
 RATES = {'vgg_16_bn': '[0.50]*7+[0.95]*5', 'resnet_56': '[0.]+[0.18]*29',
-         'resnet_110': '[0.]+[0.2]*2+[0.3]*18+[0.40]*18+[0.39]*19', 'resnet_50': '[0.]+[0.1]*3+[0.4]*7+[0.4]*9'}
+         'resnet_110': '[0.]+[0.2]*2+[0.3]*18+[0.40]*18+[0.39]*19', 'resnet_50': '[0.]+[0.1]*3+[0.4]*7+[0.4]*9',
+         'densenet_40': '[0.]+[0.2]*12+[0.]+[0.2]*12+[0.]+[0.2]*12', 'googlenet': '[0.4]+[0.85]*2+[0.9]*5+[0.9]*2',
+         'u2netp': '[0.40]*40'}
 net = sys.argv[1] if len(sys.argv) > 1 else 'resnet_50'
 dev = torch.device('cuda', 0)
 rates = get_compress_rate(RATES[net])
