@@ -1,0 +1,37 @@
+"""Score -> select -> rebuild -> fill, all on the device: the non-resume branch of the reference's `load_model`
+(/root/reference/utils/load_models.py:803-838: build the unpruned net, `imp_score` it, then `load_<net>_model` copies
+the kept filters into the pruned net), and the body of `prune_dynamic.py:150-154`'s loop, which repeats it on nets
+that are already pruned.  Scores stay on the GPU between the three steps; no score file is needed unless asked for.
+"""
+import types
+
+import torch
+
+from .compress import get_compress_rate
+from .generate import imp_score
+from .topk import kept_channels
+from .transfer import transfer_weights
+from .zoo import get_network
+
+
+def pruned_model(net_name, compress_rate, origin_model, limit=5, batch_size=128, loader=None, scores=None,
+                 input_side=None, seed=None, out_root=None):
+    """Returns (pruned net on origin_model's device, {file stem: score vector}, [(Selection, kept ids)]).
+
+    compress_rate: the reference's string form (`'[0.]+[0.18]*29'`) or a list of floats.  `scores` skips the scoring
+    pass (e.g. files of an earlier run: a directory or a {stem: vector} mapping).  `seed` seeds the pruned net's own
+    initialisation - the tensors the loaders do not fill (biases, most BatchNorms, the classifier of VGG) keep it, as in
+    the reference.  `out_root` additionally writes the reference's importance_score/<net>_limit<N>/*.npy files."""
+    device = next(origin_model.parameters()).device
+    if device.type != 'cuda':
+        raise RuntimeError('pruned_model needs the unpruned net on a CUDA device (got %s); there is no CPU fallback' % device)
+    rates = get_compress_rate(compress_rate) if isinstance(compress_rate, str) else list(compress_rate)
+    if scores is None:
+        args = types.SimpleNamespace(net=net_name, limit=limit, batch_size=batch_size, input_side=input_side)
+        scores = imp_score(origin_model, args, loader=loader, out_root=out_root or 'importance_score', write=out_root is not None)
+    kept = kept_channels(net_name, rates, scores, device=device)
+    if seed is not None:
+        torch.manual_seed(seed)
+    net = get_network(net_name, rates).to(device).eval()
+    transfer_weights(net_name, net, origin_model.state_dict(), kept)
+    return net, scores, kept

@@ -15,6 +15,10 @@
  *     without a CUDA device every compute entry returns DCTP_E_CUDA
  *   - one host thread per process drives the library (forward hooks fire on the forward thread);
  *     calls are asynchronous on `stream` unless stated otherwise
+ *   - the tensor-core score kernels are launched with programmatic stream serialization: their prologue may overlap
+ *     the tail of the preceding kernel on the stream, but they wait for that kernel (and its memory) to complete
+ *     before the first activation byte is read - ordinary stream semantics for the caller; DCTP_PDL=0 in the
+ *     environment falls back to plain launches
  */
 #ifndef DCTP_H
 #define DCTP_H
@@ -29,7 +33,8 @@ extern "C" {
 #define DCTP_E_INVALID    -1      /* bad argument (null pointer, non-positive size, window out of range) */
 #define DCTP_E_CUDA       -2      /* CUDA runtime error; text in dctp_last_error() */
 #define DCTP_E_UNSUPPORTED -3     /* shape / layout the requested kernel path does not take */
-#define DCTP_E_DEVICE     -4      /* a kernel reported a fault in the device status word (tensor-core wait timed out) */
+#define DCTP_E_DEVICE     -4      /* a kernel reported a fault in the device status word (tensor-core wait timed out,
+                                     channel index out of range in dctp_gather_weight) */
 
 /* kernel path for dctp_score_accum */
 #define DCTP_PATH_AUTO   0        /* the fastest tensor-core kernel the shape allows, CUDA cores otherwise */

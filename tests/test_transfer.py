@@ -141,3 +141,23 @@ def test_device_transfer_reproduces_reference_loader(lib, cuda_device, net):
     plan = transfer.transfer_weights(net, pruned, orig.state_dict(), kept)
     assert any(op.kind == 'gather' for op in plan)
     check_against_golden(gold, before, digests(pruned.state_dict()))
+
+
+@pytest.mark.gpu
+def test_score_select_rebuild_fill_on_device(lib, cuda_device):
+    """load_model's non-resume branch in one call: must equal scoring, top-k and transfer done step by step."""
+    from dct_pruning_b200.prune import pruned_model
+    from dct_pruning_b200.topk import kept_channels
+    torch.backends.cudnn.allow_tf32 = False
+    rate = '[0.]+[0.18]*29'
+    torch.manual_seed(0)
+    orig = get_network('resnet_56').to(cuda_device).eval()
+    net, scores, kept = pruned_model('resnet_56', rate, orig, limit=1, batch_size=8, seed=0)
+    assert len(scores) == 55 and len(kept) == 45
+    torch.manual_seed(0)
+    again = get_network('resnet_56', get_compress_rate(rate)).to(cuda_device).eval()
+    transfer.transfer_weights('resnet_56', again, orig.state_dict(), kept_channels('resnet_56', rate, scores, device=cuda_device))
+    assert digests(net.state_dict()) == digests(again.state_dict())
+    with torch.no_grad():
+        y = net(torch.randn(2, 3, 32, 32, device=cuda_device))
+    assert y.shape == (2, 10) and torch.isfinite(y).all()
