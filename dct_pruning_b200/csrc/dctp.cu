@@ -297,7 +297,7 @@ int ensure_init() {
                              reinterpret_cast<const void*>(score_t_kernel<32, 6, 1>), reinterpret_cast<const void*>(score_t_kernel<32, 6, 2>),
                              reinterpret_cast<const void*>(score_t_kernel<16, 6, 1>), reinterpret_cast<const void*>(score_t_kernel<16, 6, 2>)};
         for (const void* fn : fns) {
-            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
     }
@@ -376,9 +376,10 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
 bool t_shape_supported(int N) { return N >= 10 && N <= 64 && (N % 2) == 0; }
 bool t_shape_ok(int N) {
     if (g.t_slots <= 0 || !t_shape_supported(N)) return false;
-    // measured A/B on one B200 (tools/prof_one.py, [256,C,N,N]): 56x56 3.05 vs 2.65 TB/s, 64x64 3.43 vs 2.94; at 28x28 / 14x14 /
-    // 32x32 (6 slots) 2.36 / 2.03 / 1.79 vs 2.59 / 2.06 / 2.01 for the smem-operand kernel's multi-map packing
-    return g.t_all || N >= g.t_auto_lo;
+    // measured A/B on one B200 (tools/prof_one.py, [256,C,N,N], TB/s, this kernel vs the smem-operand kernel):
+    // 56x56 3.16 vs 2.65, 64x64 3.43 vs 2.94 (3 slots); 28x28 3.28 vs 2.68, 32x32 2.93 vs 2.41 (6 slots, cp.async staging);
+    // 14x14 / 16x16 (6 slots of 16 columns) 2.24 / 1.64 vs 2.17 / 1.64: a tie, left with the multi-map packing; 34..50 not better
+    return g.t_all || N >= g.t_auto_lo || (N >= 18 && N <= 32);
 }
 
 int launch_t(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {

@@ -79,7 +79,13 @@ struct TScoreSmem {
     static constexpr uint32_t BX_HALF = 2 * N1MAX * 128;           // data operand (hi or lo): 2 K-blocks x N1MAX rows x 128 B
     static constexpr uint32_t SLOT_BYTES = 2 * BX_HALF;
     static constexpr uint32_t C_HALF = 64 * 128;                   // stage-2 basis (hi or lo)
-    __host__ __device__ static constexpr uint32_t off_c(int nslot) { return nslot * SLOT_BYTES; }
+    // the 6-slot variants (768 threads, 80 registers each) cannot hold the next tile in registers without spilling it,
+    // which makes every load wait for its own spill store; they stage it in shared memory with cp.async instead
+    static constexpr bool STAGED = N1MAX < 64;
+    static constexpr uint32_t PF = N1MAX == 64 ? 16 : N1MAX == 32 ? 8 : 4;     // float4 of a tile per thread
+    static constexpr uint32_t STAGE_BYTES = STAGED ? PF * 128 * 16 : 0;        // per slot: fp32 tile, thread-private vectors
+    __host__ __device__ static constexpr uint32_t off_stage(int nslot) { return nslot * SLOT_BYTES; }
+    __host__ __device__ static constexpr uint32_t off_c(int nslot) { return nslot * (SLOT_BYTES + STAGE_BYTES); }
     __host__ __device__ static constexpr uint32_t off_ctrl(int nslot) { return off_c(nslot) + 2 * C_HALF; }
     __host__ __device__ static constexpr uint32_t off_red(int nslot) { return off_ctrl(nslot) + 128; }
     __host__ __device__ static constexpr uint32_t off_table(int nslot) { return off_red(nslot) + nslot * 512; }
@@ -96,7 +102,8 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     using namespace umma;
     constexpr int WPS = 4, TPS = 128;                              // one warpgroup (= all 128 TMEM lanes) per slot
     constexpr int NT = TPS * NSLOT;
-    constexpr int TSCORE_PF = N1MAX == 64 ? 16 : N1MAX == 32 ? 8 : 4;   // prefetch registers (float4) per thread: a full tile
+    constexpr int TSCORE_PF = S::PF;                               // float4 per thread: a full tile
+    constexpr bool STAGED = S::STAGED;
     constexpr uint32_t SLOT_COLS = 2 * N1MAX;
     constexpr uint32_t TMEM_COLS = 512;
     static_assert(128 + NSLOT * SLOT_COLS <= TMEM_COLS, "TMEM budget");
@@ -125,18 +132,27 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     const int first = blockIdx.x * NSLOT + (int)wg, stride = gridDim.x * NSLOT;
 
     // ---- register prefetch of a tile
-    float4 pf[TSCORE_PF];
+    [[maybe_unused]] float4 pf[STAGED ? 1 : TSCORE_PF];
     uint32_t pf_full = 0;
+    float4* stage = reinterpret_cast<float4*>(smem + S::off_stage(NSLOT) + wg * S::STAGE_BYTES) + wtid;   // (STAGED)
     auto prefetch = [&](int tile) {
         const long long elem0 = static_cast<long long>(tile) * a.G * a.NN;
         pf_full = static_cast<uint32_t>(min(static_cast<long long>(a.tile_vec), (a.total_elems - elem0) >> 2));
         const float4* src = reinterpret_cast<const float4*>(a.x_dense + elem0) + wtid;
+        if constexpr (STAGED) {
+            const uint32_t dst = smem_u32(stage);
 #pragma unroll
-        for (int u = 0; u < TSCORE_PF; ++u)
-            if (wtid + u * TPS < pf_full) pf[u] = detail::ldg_stream(src + u * TPS);
+            for (int u = 0; u < TSCORE_PF; ++u)
+                if (wtid + u * TPS < pf_full) cp_async16(dst + u * TPS * 16, src + u * TPS);
+            cp_async_commit();
+        } else {
+#pragma unroll
+            for (int u = 0; u < TSCORE_PF; ++u)
+                if (wtid + u * TPS < pf_full) pf[u] = detail::ldg_stream(src + u * TPS);
+        }
     };
     // ---- one-time setup (independent of the activation: overlaps the preceding kernel's tail under a dependent launch): zero the data operands, stage C and the scatter table, barriers, TMEM, A' into TMEM
-    for (uint32_t off = tid * 16; off < S::off_c(NSLOT); off += NT * 16)
+    for (uint32_t off = tid * 16; off < S::off_stage(NSLOT); off += NT * 16)
         *reinterpret_cast<uint4*>(smem + off) = make_uint4(0, 0, 0, 0);
     for (uint32_t i = tid; i < 64 * 8; i += NT) {
         const uint32_t n = i >> 3, c8 = i & 7;
@@ -242,9 +258,16 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
         const int maps_here = min(a.G, a.n_maps - map0);
 
         // ---- stage 0: registers (prefetched) -> bf16 hi/lo -> data operand in shared memory
+        if constexpr (STAGED) {
+            cp_async_wait_all();
 #pragma unroll
-        for (int u = 0; u < TSCORE_PF; ++u)
-            if (wtid + u * TPS < pf_full) detail::Scatter<VPE>::st(bx_hi, bx_lo, scat[wtid + u * TPS], pf[u]);
+            for (int u = 0; u < TSCORE_PF; ++u)
+                if (wtid + u * TPS < pf_full) detail::Scatter<VPE>::st(bx_hi, bx_lo, scat[wtid + u * TPS], stage[u * TPS]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < TSCORE_PF; ++u)
+                if (wtid + u * TPS < pf_full) detail::Scatter<VPE>::st(bx_hi, bx_lo, scat[wtid + u * TPS], pf[u]);
+        }
         stamp(1);
         fence_async_smem();
         tc_fence_before_sync();                                    // this warp's tcgen05.ld of the previous tile are done

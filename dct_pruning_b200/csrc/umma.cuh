@@ -90,6 +90,9 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_s
 __device__ __forceinline__ void cp_async_commit() {
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void cp_async_wait_but_one() {          // all groups but the most recent one have completed
     asm volatile("cp.async.wait_group 1;" ::: "memory");
 }
