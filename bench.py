@@ -240,7 +240,7 @@ def run_ours(args):
             return 'score_umma_kernel<128> (tcgen05, smem operands)'
         if n % 2 == 0 and 52 <= n <= 64:
             return 'score_t_kernel<64,3> (tcgen05, TMEM-resident operands, register prefetch)'
-        if n % 2 == 0 and 18 <= n <= 32:
+        if n % 2 == 0 and 10 <= n <= 32 and a.numel() * 4 >= (32 << 20):
             return 'score_t_kernel<32,6> (tcgen05, TMEM-resident operands, cp.async staging)'
         mode = 0 if n % 4 == 0 else 1 if n % 2 == 0 else 2
         return 'score_umma_kernel<64,%d,1> (tcgen05 bf16x3, smem operands, register prefetch)' % mode

@@ -65,7 +65,8 @@ struct State {
     int t_slots = 3;                                   // tile slots per CTA of the TMEM-operand kernel (DCTP_T_SLOTS=0 disables it)
     bool t_all = false;
     bool pdl = true;                                   // programmatic dependent launch of the score kernels (DCTP_PDL=0 disables)
-    int t_auto_lo = 52;                                // smallest side AUTO routes to the TMEM-operand kernel (DCTP_T_LO)
+    int t_auto_lo = 52;                                // sides from here up always go to the TMEM-operand kernel under AUTO (DCTP_T_LO)
+    long long t_min_bytes = 32ll << 20;                // smaller sides only for launches of at least this many bytes (DCTP_T_MIN_MB)
     int regs[2][6][2] = {};                            // registers/thread per (KP, load mode, prefetch) instantiation
     // scratch of dctp_score_host (grow-only)
     float* hx = nullptr; size_t hx_bytes = 0;
@@ -130,12 +131,14 @@ int get_umma_basis(int N, int KP, UmmaBasis& out) {
     return DCTP_OK;
 }
 
-inline int t_n1max(int N) { return N <= 16 ? 16 : N <= 32 ? 32 : 64; }
+// D columns per tile slot of the TMEM-operand kernel; maps of side <= 16 sit two side by side (J = 2) in a 32-column slot
+inline int t_n1max(int N) { return N <= 32 ? 32 : 64; }
+inline int t_groups(int N) { return N <= 16 ? 2 : 1; }
 
 int get_t_basis(int N, TBasis& out) {
     auto it = g.tmem.find(N);
     if (it != g.tmem.end()) { out = it->second; return DCTP_OK; }
-    const int Ms = (N + 7) / 8 * 8, G = 128 / Ms, NN = N * N, rows = t_n1max(N);
+    const int Ms = (N + 7) / 8 * 8, G = 128 / Ms, NN = N * N, rows = t_n1max(N), J = t_groups(N);
     std::vector<uint32_t> ahi(128 * 64, 0), alo(128 * 64, 0);
     std::vector<uint16_t> chi(64 * 64, 0), clo(64 * 64, 0);
     for (int gI = 0; gI < G; ++gI)
@@ -151,13 +154,13 @@ int get_t_basis(int N, TBasis& out) {
         for (int h = 0; h < N; ++h) split_bf16(dct_coef(u, h, N), chi[u * 64 + h], clo[u * 64 + h]);
     TBasis b;
     b.vpe = (N % 4 == 0) ? 1 : 2;
-    b.tile_vec = G * NN / 4;
+    b.tile_vec = G * J * NN / 4;
     const int step = 4 / b.vpe;
     std::vector<uint16_t> tab(static_cast<size_t>(b.tile_vec) * b.vpe + 8, 0);
     for (int v = 0; v < b.tile_vec; ++v)
-        for (int sI = 0; sI < b.vpe; ++sI) {
-            const int e = 4 * v + sI * step, gI = e / NN, r = e % NN;
-            tab[(size_t)v * b.vpe + sI] = static_cast<uint16_t>(detail::kmajor_off(r / N, gI * N + r % N, rows));
+        for (int sI = 0; sI < b.vpe; ++sI) {               // map t = (g, j) of the tile: operand row (j, h), contraction column (g, w)
+            const int e = 4 * v + sI * step, t = e / NN, r = e % NN, gI = t / J, j = t % J;
+            tab[(size_t)v * b.vpe + sI] = static_cast<uint16_t>(detail::kmajor_off(j * Ms + r / N, gI * N + r % N, rows));
         }
     CUDA_TRY(cudaMalloc(&b.a_hi, ahi.size() * 4));
     CUDA_TRY(cudaMalloc(&b.a_lo, alo.size() * 4));
@@ -294,14 +297,14 @@ int ensure_init() {
     if ((rc = setup_umma_all<128>(g.regs[1]))) return rc;
     {
         const void* fns[] = {reinterpret_cast<const void*>(score_t_kernel<64, 3, 1>), reinterpret_cast<const void*>(score_t_kernel<64, 3, 2>),
-                             reinterpret_cast<const void*>(score_t_kernel<32, 6, 1>), reinterpret_cast<const void*>(score_t_kernel<32, 6, 2>),
-                             reinterpret_cast<const void*>(score_t_kernel<16, 6, 1>), reinterpret_cast<const void*>(score_t_kernel<16, 6, 2>)};
+                             reinterpret_cast<const void*>(score_t_kernel<32, 6, 1>), reinterpret_cast<const void*>(score_t_kernel<32, 6, 2>)};
         for (const void* fn : fns) {
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
     }
     if (const char* e = std::getenv("DCTP_PDL")) g.pdl = std::atoi(e) != 0;
+    if (const char* e = std::getenv("DCTP_T_MIN_MB")) g.t_min_bytes = static_cast<long long>(std::atoi(e)) << 20;
     if (const char* e = std::getenv("DCTP_T_SLOTS")) g.t_slots = std::atoi(e);
     if (g.t_slots != 0) g.t_slots = 3;
     CUDA_TRY(cudaFuncSetAttribute(score_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LargeSmem::TOTAL));
@@ -378,8 +381,14 @@ bool t_shape_ok(int N) {
     if (g.t_slots <= 0 || !t_shape_supported(N)) return false;
     // measured A/B on one B200 (tools/prof_one.py, [256,C,N,N], TB/s, this kernel vs the smem-operand kernel):
     // 56x56 3.16 vs 2.65, 64x64 3.43 vs 2.94 (3 slots); 28x28 3.28 vs 2.68, 32x32 2.93 vs 2.41 (6 slots, cp.async staging);
-    // 14x14 / 16x16 (6 slots of 16 columns) 2.24 / 1.64 vs 2.17 / 1.64: a tie, left with the multi-map packing; 34..50 not better
-    return g.t_all || N >= g.t_auto_lo || (N >= 18 && N <= 32);
+    // 14x14 2.87 vs 2.18, 16x16 3.10 vs 2.58 (6 slots, two maps side by side per slot); 34..50 not better
+    return g.t_all || N >= g.t_auto_lo || N <= 32;
+}
+// ... and how much work a launch must carry before AUTO prefers it: the 6-slot variant's prologue (768 threads, A' into
+// TMEM, 96 KB of operand slots) costs a few microseconds more than the smem-operand kernel's, which decides launches of a few MB
+// (ResNet-56 [256,16,32,32] = 17 MB: 0.655 vs 0.754 ms per batch over its 55 hooks with / without this rule)
+bool t_launch_ok(int N, long long bytes) {
+    return t_shape_ok(N) && (g.t_all || N >= g.t_auto_lo || bytes >= g.t_min_bytes);
 }
 
 int launch_t(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
@@ -392,9 +401,11 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
     a.N = N; a.NN = N * N; a.Ms = (N + 7) / 8 * 8; a.G = 128 / a.Ms;
     a.total_elems = static_cast<long long>(a.n_maps) * a.NN;
     a.tile_vec = basis.tile_vec;
-    a.num_tiles = (a.n_maps + a.G - 1) / a.G;
-    a.K1S = (a.G * N + 15) / 16; a.N1 = (N + 15) / 16 * 16;
-    a.TPM = pow2_floor(128 / a.G < 32 ? 128 / a.G : 32);
+    a.J = t_groups(N); a.MT = a.G * a.J;
+    a.num_tiles = (a.n_maps + a.MT - 1) / a.MT;
+    a.K1S = (a.G * N + 15) / 16; a.N1 = a.J > 1 ? a.J * a.Ms : (N + 15) / 16 * 16;
+    a.TPM = pow2_floor(128 / a.MT < 32 ? 128 / a.MT : 32);
+    a.idesc_g = umma::make_idesc_bf16(128, 16, false, false);
     a.tpm_shift = 0;
     while ((1 << a.tpm_shift) < a.TPM) ++a.tpm_shift;
     a.idesc = umma::make_idesc_bf16(128, a.N1, false, false);
@@ -410,22 +421,18 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
     }
     a.div_ms.set(a.Ms);
     const int n1max = t_n1max(N), ns = n1max == 64 ? 3 : 6;
-    const size_t smem = n1max == 64 ? TScoreSmem<64>::total(ns, a.scatter_bytes)
-                                    : n1max == 32 ? TScoreSmem<32>::total(ns, a.scatter_bytes) : TScoreSmem<16>::total(ns, a.scatter_bytes);
+    const size_t smem = n1max == 64 ? TScoreSmem<64>::total(ns, a.scatter_bytes) : TScoreSmem<32>::total(ns, a.scatter_bytes);
     int grid = g.sm_count;
     const int need = (a.num_tiles + ns - 1) / ns;
     if (grid > need) grid = need;
-    a.chan_step = static_cast<int>((static_cast<long long>(grid) * ns * a.G) % c_count);
+    a.chan_step = static_cast<int>((static_cast<long long>(grid) * ns * a.MT) % c_count);
     const bool v2 = basis.vpe == 2;
     if (n1max == 64) {
         if (v2) CUDA_TRY(launch_score(score_t_kernel<64, 3, 2>, grid, 384, smem, stream, a));
         else CUDA_TRY(launch_score(score_t_kernel<64, 3, 1>, grid, 384, smem, stream, a));
-    } else if (n1max == 32) {
+    } else {
         if (v2) CUDA_TRY(launch_score(score_t_kernel<32, 6, 2>, grid, 768, smem, stream, a));
         else CUDA_TRY(launch_score(score_t_kernel<32, 6, 1>, grid, 768, smem, stream, a));
-    } else {
-        if (v2) CUDA_TRY(launch_score(score_t_kernel<16, 6, 2>, grid, 768, smem, stream, a));
-        else CUDA_TRY(launch_score(score_t_kernel<16, 6, 1>, grid, 768, smem, stream, a));
     }
     if (tracing) {
         long long h[256];
@@ -477,7 +484,7 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
     const float* first = x + static_cast<long long>(c_begin) * stride_c;
     const bool dense = basis.scatter != nullptr && stride_c == a.NN && (B == 1 || stride_b == static_cast<long long>(c_count) * a.NN) &&
                        (reinterpret_cast<uintptr_t>(first) % 16) == 0;
-    if (KP == 64 && allow_t && dense && t_shape_ok(N))
+    if (KP == 64 && allow_t && dense && t_launch_ok(N, static_cast<long long>(a.n_maps) * a.NN * 4))
         return launch_t(first, B, N, c_count, accum, energy_out, coeff_out, stream);
     int mode;
     if (dense) {

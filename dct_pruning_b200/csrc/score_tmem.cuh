@@ -53,13 +53,15 @@ struct TScoreArgs {
     long long total_elems;          // n_maps * NN
     int n_maps, c_count;
     int N, NN, Ms, G;
-    int tile_vec;                   // float4 vectors per full tile = G*NN/4
+    int J, MT;                      // column groups of a tile (maps side by side along the D columns; 1 or 2) and maps per tile = G * J
+    int tile_vec;                   // float4 vectors per full tile = MT*NN/4
     int num_tiles;
     int K1S;                        // stage-1 k-steps = ceil(G*N / 16)
-    int N1;                         // N rounded up to 16: MMA N of both stages, contraction length of stage 2
+    int N1;                         // MMA N of stage 1 = D columns in use: N rounded up to 16 (J = 1) or J * Ms (J = 2)
     int TPM, tpm_shift;             // threads per map in the final reduction (power of two), its log2
     int chan_step;                  // (tiles between a slot's consecutive tiles * G) mod c_count
     uint32_t idesc;                 // M = 128, N = N1, bf16 x bf16 -> f32, K-major B
+    uint32_t idesc_g;               // J = 2: stage 2 runs per column group, N = Ms
     const uint16_t* scatter;        // [tile_vec][VPE] byte offsets of each float4's pieces in the K-major data operand
     uint32_t scatter_bytes;
     const uint32_t* a_hi;           // [128][64] packed bf16 pairs of A' = I_G (x) C_N (row (g,v), column pair (g',w)/2)
@@ -82,19 +84,19 @@ struct TScoreSmem {
     // the 6-slot variants (768 threads, 80 registers each) cannot hold the next tile in registers without spilling it,
     // which makes every load wait for its own spill store; they stage it in shared memory with cp.async instead
     static constexpr bool STAGED = N1MAX < 64;
-    static constexpr uint32_t PF = N1MAX == 64 ? 16 : N1MAX == 32 ? 8 : 4;     // float4 of a tile per thread
+    static constexpr uint32_t PF = N1MAX == 64 ? 16 : 8;                       // float4 of a tile per thread
     static constexpr uint32_t STAGE_BYTES = STAGED ? PF * 128 * 16 : 0;        // per slot: fp32 tile, thread-private vectors
     __host__ __device__ static constexpr uint32_t off_stage(int nslot) { return nslot * SLOT_BYTES; }
     __host__ __device__ static constexpr uint32_t off_c(int nslot) { return nslot * (SLOT_BYTES + STAGE_BYTES); }
     __host__ __device__ static constexpr uint32_t off_ctrl(int nslot) { return off_c(nslot) + 2 * C_HALF; }
     __host__ __device__ static constexpr uint32_t off_red(int nslot) { return off_ctrl(nslot) + 128; }
-    __host__ __device__ static constexpr uint32_t off_table(int nslot) { return off_red(nslot) + nslot * 512; }
+    __host__ __device__ static constexpr uint32_t off_table(int nslot) { return off_red(nslot) + nslot * 1024; }   // 2 x 128 floats per slot
     __host__ __device__ static constexpr uint32_t total(int nslot, uint32_t table_bytes) {
         return off_table(nslot) + ((table_bytes + 15u) & ~15u);
     }
 };
 
-// N1MAX: widest accumulator a slot holds (64 / 32 / 16 columns); NSLOT tile slots per CTA (one warpgroup each);
+// N1MAX: widest accumulator a slot holds (64 / 32 columns); NSLOT tile slots per CTA (one warpgroup each);
 // VPE: scatter pieces per float4 (1: N % 4 == 0, one 8-byte store; 2: N even, two 4-byte stores)
 template <int N1MAX, int NSLOT, int VPE>
 __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArgs a) {
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     uint8_t* c_lo = c_hi + S::C_HALF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_ctrl(NSLOT));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_ctrl(NSLOT) + 64);
-    float* red = reinterpret_cast<float*>(smem + S::off_red(NSLOT)) + wg * 128;
+    float* red = reinterpret_cast<float*>(smem + S::off_red(NSLOT)) + wg * 256;      // [column group][lane]
     const Entry* scat = reinterpret_cast<const Entry*>(smem + S::off_table(NSLOT));
     uint64_t* bar = bars + wg;
 
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     uint32_t pf_full = 0;
     float4* stage = reinterpret_cast<float4*>(smem + S::off_stage(NSLOT) + wg * S::STAGE_BYTES) + wtid;   // (STAGED)
     auto prefetch = [&](int tile) {
-        const long long elem0 = static_cast<long long>(tile) * a.G * a.NN;
+        const long long elem0 = static_cast<long long>(tile) * a.MT * a.NN;
         pf_full = static_cast<uint32_t>(min(static_cast<long long>(a.tile_vec), (a.total_elems - elem0) >> 2));
         const float4* src = reinterpret_cast<const float4*>(a.x_dense + elem0) + wtid;
         if constexpr (STAGED) {
@@ -223,6 +225,13 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     auto issue_stage2 = [&]() {                                    // D2 = A2 * C^T : A2hi*Chi + A2lo*Chi + A2hi*Clo
         tc_fence_after_sync();
         const uint32_t c_hi_lo = k_lo + lo_c_hi, c_lo_lo = k_lo + lo_c_lo;
+        if (a.J > 1) {                                             // per column group j: D2[:, (j,u)] = A2[:, (j,h)] * C[u,h]^T, Ms = 16
+            for (int j = 0; j < a.J; ++j)
+                detail::issue_ts3<1, 0>(d_col + 16 * j, a2_hi_col + 8 * j, a2_lo_col + 8 * j, a2_hi_col + 8 * j, c_hi_lo, c_hi_lo,
+                                        c_lo_lo, desc_k, a.idesc_g);
+            mma_commit(bar);
+            return;
+        }
         switch (a.N1 >> 4) {
             case 1: detail::issue_ts3<1, 0>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
             case 2: if constexpr (N1MAX >= 32) detail::issue_ts3<2, 0>(d_col, a2_hi_col, a2_lo_col, a2_hi_col, c_hi_lo, c_hi_lo, c_lo_lo, desc_k, a.idesc); break;
@@ -244,9 +253,11 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
 
     // final reduction roles, fixed for the whole kernel
     const uint32_t tpm = a.TPM;
-    const uint32_t red_t = wtid >> a.tpm_shift, red_sub = wtid & (tpm - 1);
-    const float* red_row = red + min(red_t, (uint32_t)a.G - 1) * a.Ms;
-    uint32_t chan = (uint32_t)((static_cast<long long>(first) * a.G + red_t) % a.c_count);
+    const uint32_t red_t = wtid >> a.tpm_shift, red_sub = wtid & (tpm - 1);          // map t of the tile = (g, j), t = g * J + j
+    const uint32_t red_tc = min(red_t, (uint32_t)a.MT - 1);
+    const uint32_t red_g = a.J > 1 ? red_tc >> 1 : red_tc, red_j = a.J > 1 ? red_tc & 1u : 0u;
+    const float* red_row = red + red_j * 128 + red_g * a.Ms;
+    uint32_t chan = (uint32_t)((static_cast<long long>(first) * a.MT + red_t) % a.c_count);
 
     int trace_i = 0;
     auto stamp = [&](int k) {
@@ -254,8 +265,8 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     };
     for (int tile = first; tile < a.num_tiles; tile += stride) {
         stamp(0);
-        const int map0 = tile * a.G;
-        const int maps_here = min(a.G, a.n_maps - map0);
+        const int map0 = tile * a.MT;
+        const int maps_here = min(a.MT, a.n_maps - map0);
 
         // ---- stage 0: registers (prefetched) -> bf16 hi/lo -> data operand in shared memory
         if constexpr (STAGED) {
@@ -343,16 +354,24 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
                     e0 = fmaf(z0, z0, e0);
                     e1 = fmaf(z1, z1, e1);
                 }
-                if (a.dump != nullptr && lane_in_map && (int)my_g < maps_here) {
+                if (a.dump != nullptr && lane_in_map) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const uint32_t u = part * 32 + i;
-                        if (u < (uint32_t)a.N) a.dump[(long long)(map0 + my_g) * a.NN + u * a.N + my_v] = __uint_as_float(r[i >> 4][i & 15]);
+                        const uint32_t col = part * 32 + i;
+                        const uint32_t j = a.J > 1 ? col >> 4 : 0u, u = a.J > 1 ? col & 15u : col;    // column group, coefficient row
+                        const int t = (int)(my_g * a.J + j);
+                        if (u < (uint32_t)a.N && j < (uint32_t)a.J && t < maps_here)
+                            a.dump[(long long)(map0 + t) * a.NN + u * a.N + my_v] = __uint_as_float(r[i >> 4][i & 15]);
                     }
                 }
             }
         }
-        red[wtid] = e0 + e1;
+        if (a.J > 1) {                                             // (N1MAX = 32: r[0] was column group 0, r[1] group 1)
+            red[wtid] = e0;
+            red[128 + wtid] = e1;
+        } else {
+            red[wtid] = e0 + e1;
+        }
         named_bar_sync(bar_id, TPS);
         {
             // TPM threads per map, fixed summation order -> bit-reproducible per-map energy
