@@ -8,7 +8,7 @@ dev = torch.device('cuda', 0)
 for n in (int(v) for v in sys.argv[1:]):
     g = torch.Generator().manual_seed(n)
     x = torch.relu(torch.randn(1, 2, n, n, generator=g))
-    _, en, co = dct_energy(x.to(dev), path='umma', want_energy=True, want_coeff=True)
+    _, en, co = dct_energy(x.to(dev), path='tmem', want_energy=True, want_coeff=True)
     got = co.cpu().numpy()[0, 0].astype(np.float64)
     want = dctn(x.numpy()[0, 0].astype(np.float64), type=2, norm='ortho')
     tol = 1e-3 * np.abs(want).max()
@@ -33,7 +33,7 @@ if os.environ.get('DCTP_T_DUMP_STAGE') == '1':
     for n in (int(v) for v in sys.argv[1:]):
         g = torch.Generator().manual_seed(n)
         x = torch.relu(torch.randn(1, 2, n, n, generator=g))
-        _, _, co = dct_energy(x.to(dev), path='umma', want_coeff=True)
+        _, _, co = dct_energy(x.to(dev), path='tmem', want_coeff=True)
         got = co.cpu().numpy()[0, 0].astype(np.float64)          # [v][h] = (C X^T)
         kk = np.arange(n)[:, None]; mm = np.arange(n)[None, :]
         C = np.cos(np.pi * (2 * mm + 1) * kk / (2 * n)) * np.sqrt(2.0 / n); C[0] *= np.sqrt(0.5)
