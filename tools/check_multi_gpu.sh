@@ -18,6 +18,8 @@ names = sorted(f for f in os.listdir(a) if f.endswith('.npy'))
 assert names == sorted(f for f in os.listdir(b) if f.endswith('.npy')) and len(names) == 55
 same = sum(open(os.path.join(a, f), 'rb').read() == open(os.path.join(b, f), 'rb').read() for f in names)
 worst = max(np.abs(np.load(os.path.join(a, f)) - np.load(os.path.join(b, f))).max() / max(np.load(os.path.join(a, f)).max(), 1e-30) for f in names)
-print('score files byte-identical 1 vs $N ranks: %d of %d (worst rel diff %.2e)' % (same, len(names), worst))
+print('score files byte-identical 1 vs $N ranks: %d of %d (worst rel diff %.2e; a per-rank batch of 64/$N images makes cuDNN pick other '
+      'convolution algorithms than 64, so the ACTIVATIONS may differ in the last bits; the scoring itself is rank-count independent)' % (same, len(names), worst))
+assert worst < 1e-5
 print('kept_channels.json identical:', open(a + '/kept_channels.json').read() == open(b + '/kept_channels.json').read())
 PY
