@@ -232,7 +232,7 @@ def run_ours(args):
     # which kernel a site's launch runs (mirrors the dispatch in csrc/dctp.cu for dense activations)
     def kernel_of(a):
         n = a.shape[2]
-        if a.shape[2] == a.shape[3] and 128 < n <= 320 and n % 16 == 0:
+        if a.shape[2] == a.shape[3] and 96 <= n <= 320 and n % 16 == 0:
             return 'score_large_kernel (tcgen05, tiled, 16 warps)'
         if a.shape[2] != a.shape[3] or n > 128:
             return 'score_simt_kernel (fp32 CUDA cores)'

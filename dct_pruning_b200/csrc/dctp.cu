@@ -66,6 +66,9 @@ struct State {
     bool t_all = false;
     bool pdl = true;                                   // programmatic dependent launch of the score kernels (DCTP_PDL=0 disables)
     int t_auto_lo = 52;                                // sides from here up always go to the TMEM-operand kernel under AUTO (DCTP_T_LO)
+    int large_lo = 96;                                 // smallest side AUTO routes to the tiled large-map kernel (DCTP_LARGE_LO);
+                                                       // measured vs the smem-operand kernel, [12,64,N,N]: 80 0.66 vs 0.65, 96 0.87 vs 0.73,
+                                                       // 112 1.07 vs 0.77, 128 1.43 vs 0.89 TB/s
     long long t_min_bytes = 32ll << 20;                // smaller sides only for launches of at least this many bytes (DCTP_T_MIN_MB)
     int regs[2][6][2] = {};                            // registers/thread per (KP, load mode, prefetch) instantiation
     // scratch of dctp_score_host (grow-only)
@@ -304,6 +307,7 @@ int ensure_init() {
         }
     }
     if (const char* e = std::getenv("DCTP_PDL")) g.pdl = std::atoi(e) != 0;
+    if (const char* e = std::getenv("DCTP_LARGE_LO")) g.large_lo = std::atoi(e);
     if (const char* e = std::getenv("DCTP_T_MIN_MB")) g.t_min_bytes = static_cast<long long>(std::atoi(e)) << 20;
     if (const char* e = std::getenv("DCTP_T_SLOTS")) g.t_slots = std::atoi(e);
     if (g.t_slots != 0) g.t_slots = 3;
@@ -336,7 +340,9 @@ int pick_vec(const float* x, long long stride_b, long long stride_c, int c_begin
 
 // TMEM-operand kernel: dense tensors, N % 4 == 0, 16 <= N <= 64
 // large-map tensor-core kernel: dense square maps, 128 < N <= 320, N % 16 == 0
-bool large_shape_ok(int H, int W, long long stride_h) { return H == W && H > 128 && H <= 320 && (H % 16) == 0 && stride_h == W; }
+// the tiled large-map kernel takes dense square maps of side 80..320 (multiples of 16); AUTO gives it everything above large_lo
+bool large_shape_supported(int H, int W, long long stride_h) { return H == W && H >= 80 && H <= 320 && (H % 16) == 0 && stride_h == W; }
+bool large_shape_ok(int H, int W, long long stride_h) { return large_shape_supported(H, W, stride_h) && H >= g.large_lo; }
 
 int launch_large(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
     LargeBasis basis;
@@ -558,8 +564,8 @@ int launch_simt(const float* x, int B, int H, int W, long long stride_b, long lo
 
 int resolve_path(int path, int H, int W, long long stride_h) {
     if (path == DCTP_PATH_AUTO) {
-        if (umma_shape_ok(H, W, stride_h)) return DCTP_PATH_UMMA;
         if (large_shape_ok(H, W, stride_h)) return DCTP_PATH_LARGE;
+        if (umma_shape_ok(H, W, stride_h)) return DCTP_PATH_UMMA;
         return DCTP_PATH_SIMT;
     }
     return path;
@@ -622,6 +628,10 @@ int dctp_prepare(int H, int W) {
             int rc2 = get_t_basis(H, tb);
             if (rc2) return rc2;
         }
+        if (large_shape_ok(H, W, W)) {
+            LargeBasis lb;
+            if ((rc = get_large_basis(H, lb))) return rc;
+        }
         UmmaBasis b;
         return get_umma_basis(H, H <= 64 ? 64 : 128, b);
     }
@@ -668,10 +678,12 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
             const float* first = x + static_cast<long long>(c_begin) * stride_c;
             const bool dense = stride_c == static_cast<long long>(H) * W && (B == 1 || stride_b == static_cast<long long>(c_count) * H * W) &&
                                (reinterpret_cast<uintptr_t>(first) % 16) == 0;
-            if (!large_shape_ok(H, W, stride_h) || !dense) {
-                if (path == DCTP_PATH_AUTO)              // windows / strided batches of large maps: CUDA cores
+            if (!(path == DCTP_PATH_AUTO ? large_shape_ok(H, W, stride_h) : large_shape_supported(H, W, stride_h)) || !dense) {
+                if (path == DCTP_PATH_AUTO && umma_shape_ok(H, W, stride_h))   // windows / strided batches: the smem-operand kernel ...
+                    return launch_umma<128>(x, B, H, stride_b, stride_c, c_begin, c_count, accum, energy_out, coeff_out, s, false);
+                if (path == DCTP_PATH_AUTO)              // ... or, above its range, CUDA cores
                     return launch_simt(x, B, H, W, stride_b, stride_c, stride_h, c_begin, c_count, accum, energy_out, coeff_out, s);
-                return fail(DCTP_E_UNSUPPORTED, "large-map path takes dense 16-B aligned square maps, side 144..320 multiple of 16 (got %dx%d)", H, W);
+                return fail(DCTP_E_UNSUPPORTED, "large-map path takes dense 16-B aligned square maps, side 80..320 multiple of 16 (got %dx%d)", H, W);
             }
             return launch_large(first, B, H, c_count, accum, energy_out, coeff_out, s);
         }

@@ -102,7 +102,7 @@ def test_general_shapes_on_cuda_cores(lib, cuda_device, shape):
         assert np.abs(co.cpu().numpy() - z).max() / np.abs(z).max() < 2e-5
 
 
-@pytest.mark.parametrize('n', [144, 160, 176, 256, 288, 320])
+@pytest.mark.parametrize('n', [80, 96, 112, 128, 144, 160, 176, 256, 288, 320])
 def test_large_map_kernel(lib, cuda_device, n):
     """Tiled tensor-core kernel for U^2-Netp's large stages: energies vs the float64 oracle and vs the CUDA-core
     kernel, coefficients vs scipy, several maps per channel and more work items than SMs."""
