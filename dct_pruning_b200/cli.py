@@ -29,6 +29,9 @@ def build_parser():
     p.add_argument('--net', type=str, default='googlenet', choices=tuple(NETS), help='net type')
     # opt-in extras
     p.add_argument('--compress_rate', type=str, default=None, help="e.g. '[0.]+[0.18]*29': also write kept_channels.json")
+    p.add_argument('--save_pruned', type=str, default=None,
+                   help='with --compress_rate: also build the pruned net, fill it from the scored one on the device '
+                        '(what load_model does before fine-tuning) and torch.save its state dict here')
     p.add_argument('--seed', type=int, default=0, help='seed of the random-init weights when no checkpoint is found')
     p.add_argument('--out_root', type=str, default='importance_score')
     p.add_argument('--input_side', type=int, default=None, help='override the input resolution (e.g. 288 for DUTS crops)')
@@ -70,6 +73,15 @@ def main(argv=None):
                        'selections': [{'file': s.stem, 'conv': s.conv, 'C': s.C, 'k': s.k,
                                        'select_index': [int(i) for i in idx]} for s, idx in kept]}, f)
         print('kept-channel sets ->', path)
+        if args.save_pruned:
+            from .compress import get_compress_rate
+            from .transfer import transfer_weights
+            torch.manual_seed(args.seed)
+            pruned = get_network(args.net, get_compress_rate(args.compress_rate)).to(device).eval()
+            transfer_weights(args.net, pruned, net.state_dict(), kept)
+            torch.save({k: v.cpu() for k, v in pruned.state_dict().items()}, args.save_pruned)
+            print('pruned %s (%d parameters, was %d) ->' % (args.net, sum(p.numel() for p in pruned.parameters()),
+                                                           sum(p.numel() for p in net.parameters())), args.save_pruned)
     if rank == 0:
         print('The importance score of %s has generated completed!' % args.net)
     ddist.shutdown()
