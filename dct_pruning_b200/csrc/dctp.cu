@@ -136,7 +136,7 @@ int get_umma_basis(int N, int KP, UmmaBasis& out) {
 
 // D columns per tile slot of the TMEM-operand kernel; maps of side <= 16 sit two side by side (J = 2) in a 32-column slot
 inline int t_n1max(int N) { return N <= 32 ? 32 : 64; }
-inline int t_groups(int N) { return N <= 16 ? 2 : 1; }
+inline int t_groups(int N) { return N <= 8 ? 4 : N <= 16 ? 2 : 1; }
 
 int get_t_basis(int N, TBasis& out) {
     auto it = g.tmem.find(N);
@@ -153,10 +153,11 @@ int get_t_basis(int N, TBasis& out) {
                 ahi[row * 64 + k / 2] |= static_cast<uint32_t>(h) << (16 * (k & 1));
                 alo[row * 64 + k / 2] |= static_cast<uint32_t>(l) << (16 * (k & 1));
             }
-    for (int u = 0; u < N; ++u)
-        for (int h = 0; h < N; ++h) split_bf16(dct_coef(u, h, N), chi[u * 64 + h], clo[u * 64 + h]);
+    for (int rep = 0; rep < (Ms == 8 ? 2 : 1); ++rep)           // Ms = 8: two maps share a 16-column stage-2 group -> I_2 (x) C_N
+        for (int u = 0; u < N; ++u)
+            for (int h = 0; h < N; ++h) split_bf16(dct_coef(u, h, N), chi[(rep * 8 + u) * 64 + rep * 8 + h], clo[(rep * 8 + u) * 64 + rep * 8 + h]);
     TBasis b;
-    b.vpe = (N % 4 == 0) ? 1 : 2;
+    b.vpe = (N % 4 == 0) ? 1 : (N % 2 == 0) ? 2 : 4;
     b.tile_vec = G * J * NN / 4;
     const int step = 4 / b.vpe;
     std::vector<uint16_t> tab(static_cast<size_t>(b.tile_vec) * b.vpe + 8, 0);
@@ -300,7 +301,8 @@ int ensure_init() {
     if ((rc = setup_umma_all<128>(g.regs[1]))) return rc;
     {
         const void* fns[] = {reinterpret_cast<const void*>(score_t_kernel<64, 3, 1>), reinterpret_cast<const void*>(score_t_kernel<64, 3, 2>),
-                             reinterpret_cast<const void*>(score_t_kernel<32, 6, 1>), reinterpret_cast<const void*>(score_t_kernel<32, 6, 2>)};
+                             reinterpret_cast<const void*>(score_t_kernel<32, 6, 1>), reinterpret_cast<const void*>(score_t_kernel<32, 6, 2>),
+                             reinterpret_cast<const void*>(score_t_kernel<32, 6, 4>)};
         for (const void* fn : fns) {
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -381,8 +383,9 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
     return DCTP_OK;
 }
 
-// which maps the TMEM-operand kernel takes at all (dense, even side 10..64), and which ones AUTO gives it
-bool t_shape_supported(int N) { return N >= 10 && N <= 64 && (N % 2) == 0; }
+// which maps the TMEM-operand kernel takes at all (dense; side 5..64, odd sides up to 13 and only when the whole stream is a
+// multiple of four floats), and which ones AUTO gives it
+bool t_shape_supported(int N) { return N >= 5 && N <= 64 && ((N % 2) == 0 || N <= 13); }   // (odd sides: 8-byte scatter entries must fit in shared memory)
 bool t_shape_ok(int N) {
     if (g.t_slots <= 0 || !t_shape_supported(N)) return false;
     // measured A/B on one B200 (tools/prof_one.py, [256,C,N,N], TB/s, this kernel vs the smem-operand kernel):
@@ -393,8 +396,12 @@ bool t_shape_ok(int N) {
 // ... and how much work a launch must carry before AUTO prefers it: the 6-slot variant's prologue (768 threads, A' into
 // TMEM, 96 KB of operand slots) costs a few microseconds more than the smem-operand kernel's, which decides launches of a few MB
 // (ResNet-56 [256,16,32,32] = 17 MB: 0.655 vs 0.754 ms per batch over its 55 hooks with / without this rule)
+// odd sides: a float4 of the stream may straddle maps, the stream itself must not end inside one
+bool t_stream_ok(int N, long long n_maps) { return (N % 2) == 0 || (n_maps * N * N) % 4 == 0; }
 bool t_launch_ok(int N, long long bytes) {
-    return t_shape_ok(N) && (g.t_all || N >= g.t_auto_lo || bytes >= g.t_min_bytes);
+    // (sides <= 8, four maps side by side per slot, are supported but not routed: inside ResNet-50's step, with the input coming
+    //  from HBM rather than a warm L2, [256,2048,7,7] takes 69 us with either kernel)
+    return t_shape_ok(N) && (g.t_all || N >= g.t_auto_lo || (N >= 10 && bytes >= g.t_min_bytes));
 }
 
 int launch_t(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
@@ -412,6 +419,9 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
     a.K1S = (a.G * N + 15) / 16; a.N1 = a.J > 1 ? a.J * a.Ms : (N + 15) / 16 * 16;
     a.TPM = pow2_floor(128 / a.MT < 32 ? 128 / a.MT : 32);
     a.idesc_g = umma::make_idesc_bf16(128, 16, false, false);
+    a.NQ = a.N1 / 16;
+    a.j_shift = a.J == 4 ? 2 : a.J == 2 ? 1 : 0;
+    a.ms_shift = a.Ms == 8 ? 3 : 4;
     a.tpm_shift = 0;
     while ((1 << a.tpm_shift) < a.TPM) ++a.tpm_shift;
     a.idesc = umma::make_idesc_bf16(128, a.N1, false, false);
@@ -437,7 +447,8 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
         if (v2) CUDA_TRY(launch_score(score_t_kernel<64, 3, 2>, grid, 384, smem, stream, a));
         else CUDA_TRY(launch_score(score_t_kernel<64, 3, 1>, grid, 384, smem, stream, a));
     } else {
-        if (v2) CUDA_TRY(launch_score(score_t_kernel<32, 6, 2>, grid, 768, smem, stream, a));
+        if (basis.vpe == 4) CUDA_TRY(launch_score(score_t_kernel<32, 6, 4>, grid, 768, smem, stream, a));
+        else if (v2) CUDA_TRY(launch_score(score_t_kernel<32, 6, 2>, grid, 768, smem, stream, a));
         else CUDA_TRY(launch_score(score_t_kernel<32, 6, 1>, grid, 768, smem, stream, a));
     }
     if (tracing) {
@@ -490,7 +501,7 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
     const float* first = x + static_cast<long long>(c_begin) * stride_c;
     const bool dense = basis.scatter != nullptr && stride_c == a.NN && (B == 1 || stride_b == static_cast<long long>(c_count) * a.NN) &&
                        (reinterpret_cast<uintptr_t>(first) % 16) == 0;
-    if (KP == 64 && allow_t && dense && t_launch_ok(N, static_cast<long long>(a.n_maps) * a.NN * 4))
+    if (KP == 64 && allow_t && dense && t_stream_ok(N, a.n_maps) && t_launch_ok(N, static_cast<long long>(a.n_maps) * a.NN * 4))
         return launch_t(first, B, N, c_count, accum, energy_out, coeff_out, stream);
     int mode;
     if (dense) {
@@ -670,8 +681,9 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
             const float* first = x + static_cast<long long>(c_begin) * stride_c;
             const bool dense = stride_h == W && stride_c == static_cast<long long>(H) * W &&
                                (B == 1 || stride_b == static_cast<long long>(c_count) * H * W) && (reinterpret_cast<uintptr_t>(first) % 16) == 0;
-            if (H != W || !t_shape_supported(H) || !dense)
-                return fail(DCTP_E_UNSUPPORTED, "TMEM-operand path takes dense 16-B aligned square maps, even side 10..64 (got %dx%d)", H, W);
+            if (H != W || !t_shape_supported(H) || !dense || !t_stream_ok(H, static_cast<long long>(B) * c_count))
+                return fail(DCTP_E_UNSUPPORTED, "TMEM-operand path takes dense 16-B aligned square maps of side 5..64 (odd sides: up to 13, and a whole "
+                                                "number of float4 in the call) (got %dx%d)", H, W);
             return launch_t(first, B, H, c_count, accum, energy_out, coeff_out, s);
         }
         case DCTP_PATH_LARGE: {

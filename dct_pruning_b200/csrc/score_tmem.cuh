@@ -53,7 +53,9 @@ struct TScoreArgs {
     long long total_elems;          // n_maps * NN
     int n_maps, c_count;
     int N, NN, Ms, G;
-    int J, MT;                      // column groups of a tile (maps side by side along the D columns; 1 or 2) and maps per tile = G * J
+    int J, MT;                      // maps side by side along the D columns (1, 2 for Ms = 16, 4 for Ms = 8) and maps per tile = G * J
+    int j_shift, ms_shift;          // log2(J), log2(Ms) (used when J > 1)
+    int NQ;                         // J > 1: 16-column groups stage 2 runs over (N1 / 16); with Ms = 8 a group holds two maps
     int tile_vec;                   // float4 vectors per full tile = MT*NN/4
     int num_tiles;
     int K1S;                        // stage-1 k-steps = ceil(G*N / 16)
@@ -61,12 +63,12 @@ struct TScoreArgs {
     int TPM, tpm_shift;             // threads per map in the final reduction (power of two), its log2
     int chan_step;                  // (tiles between a slot's consecutive tiles * G) mod c_count
     uint32_t idesc;                 // M = 128, N = N1, bf16 x bf16 -> f32, K-major B
-    uint32_t idesc_g;               // J = 2: stage 2 runs per column group, N = Ms
+    uint32_t idesc_g;               // J > 1: stage 2 runs per 16-column group, N = 16
     const uint16_t* scatter;        // [tile_vec][VPE] byte offsets of each float4's pieces in the K-major data operand
     uint32_t scatter_bytes;
     const uint32_t* a_hi;           // [128][64] packed bf16 pairs of A' = I_G (x) C_N (row (g,v), column pair (g',w)/2)
     const uint32_t* a_lo;
-    const uint16_t* c_hi;           // [64][64] bf16 C_N zero padded (row u, column h)
+    const uint16_t* c_hi;           // [64][64] bf16 C_N zero padded (row u, column h); Ms = 8: I_2 (x) C_N in the top-left 16 x 16
     const uint16_t* c_lo;
     double* accum;
     float* energy_out;
@@ -90,14 +92,14 @@ struct TScoreSmem {
     __host__ __device__ static constexpr uint32_t off_c(int nslot) { return nslot * (SLOT_BYTES + STAGE_BYTES); }
     __host__ __device__ static constexpr uint32_t off_ctrl(int nslot) { return off_c(nslot) + 2 * C_HALF; }
     __host__ __device__ static constexpr uint32_t off_red(int nslot) { return off_ctrl(nslot) + 128; }
-    __host__ __device__ static constexpr uint32_t off_table(int nslot) { return off_red(nslot) + nslot * 1024; }   // 2 x 128 floats per slot
+    __host__ __device__ static constexpr uint32_t off_table(int nslot) { return off_red(nslot) + nslot * 2048; }   // 4 x 128 floats per slot
     __host__ __device__ static constexpr uint32_t total(int nslot, uint32_t table_bytes) {
         return off_table(nslot) + ((table_bytes + 15u) & ~15u);
     }
 };
 
 // N1MAX: widest accumulator a slot holds (64 / 32 columns); NSLOT tile slots per CTA (one warpgroup each);
-// VPE: scatter pieces per float4 (1: N % 4 == 0, one 8-byte store; 2: N even, two 4-byte stores)
+// VPE: scatter pieces per float4 (1: N % 4 == 0, one 8-byte store; 2: N even, two 4-byte stores; 4: N odd, four 2-byte stores)
 template <int N1MAX, int NSLOT, int VPE>
 __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArgs a) {
     using S = TScoreSmem<N1MAX>;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     uint8_t* c_lo = c_hi + S::C_HALF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_ctrl(NSLOT));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_ctrl(NSLOT) + 64);
-    float* red = reinterpret_cast<float*>(smem + S::off_red(NSLOT)) + wg * 256;      // [column group][lane]
+    float* red = reinterpret_cast<float*>(smem + S::off_red(NSLOT)) + wg * 512;      // [map column j][lane]
     const Entry* scat = reinterpret_cast<const Entry*>(smem + S::off_table(NSLOT));
     uint64_t* bar = bars + wg;
 
@@ -225,8 +227,8 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     auto issue_stage2 = [&]() {                                    // D2 = A2 * C^T : A2hi*Chi + A2lo*Chi + A2hi*Clo
         tc_fence_after_sync();
         const uint32_t c_hi_lo = k_lo + lo_c_hi, c_lo_lo = k_lo + lo_c_lo;
-        if (a.J > 1) {                                             // per column group j: D2[:, (j,u)] = A2[:, (j,h)] * C[u,h]^T, Ms = 16
-            for (int j = 0; j < a.J; ++j)
+        if (a.J > 1) {                                             // per 16-column group: D2[:, (j,u)] = A2[:, (j,h)] * C[u,h]^T
+            for (int j = 0; j < a.NQ; ++j)
                 detail::issue_ts3<1, 0>(d_col + 16 * j, a2_hi_col + 8 * j, a2_lo_col + 8 * j, a2_hi_col + 8 * j, c_hi_lo, c_hi_lo,
                                         c_lo_lo, desc_k, a.idesc_g);
             mma_commit(bar);
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     const uint32_t tpm = a.TPM;
     const uint32_t red_t = wtid >> a.tpm_shift, red_sub = wtid & (tpm - 1);          // map t of the tile = (g, j), t = g * J + j
     const uint32_t red_tc = min(red_t, (uint32_t)a.MT - 1);
-    const uint32_t red_g = a.J > 1 ? red_tc >> 1 : red_tc, red_j = a.J > 1 ? red_tc & 1u : 0u;
+    const uint32_t red_g = red_tc >> a.j_shift, red_j = red_tc & ((uint32_t)a.J - 1u);
     const float* red_row = red + red_j * 128 + red_g * a.Ms;
     uint32_t chan = (uint32_t)((static_cast<long long>(first) * a.MT + red_t) % a.c_count);
 
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
         stamp(6);
 
         // ---- epilogue 2: coefficients -> energy.  Lane = (g, v), column = u.
-        float e0 = 0.f, e1 = 0.f;
+        float e0 = 0.f, e1 = 0.f, f0 = 0.f, f1 = 0.f;              // columns [0,8) / [16,24) and [8,16) / [24,32) of a part
 #pragma unroll
         for (int pi = 0; pi < PARTS; ++pi) {
             const int part = part0 + pi;
@@ -349,16 +351,19 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
                 }
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     const float z0 = __uint_as_float(r[0][i]), z1 = __uint_as_float(r[1][i]);
+                    const float y0 = __uint_as_float(r[0][8 + i]), y1 = __uint_as_float(r[1][8 + i]);
                     e0 = fmaf(z0, z0, e0);
                     e1 = fmaf(z1, z1, e1);
+                    f0 = fmaf(y0, y0, f0);
+                    f1 = fmaf(y1, y1, f1);
                 }
                 if (a.dump != nullptr && lane_in_map) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const uint32_t col = part * 32 + i;
-                        const uint32_t j = a.J > 1 ? col >> 4 : 0u, u = a.J > 1 ? col & 15u : col;    // column group, coefficient row
+                        const uint32_t j = a.J > 1 ? col >> a.ms_shift : 0u, u = a.J > 1 ? col & ((uint32_t)a.Ms - 1u) : col;   // map column, coefficient row
                         const int t = (int)(my_g * a.J + j);
                         if (u < (uint32_t)a.N && j < (uint32_t)a.J && t < maps_here)
                             a.dump[(long long)(map0 + t) * a.NN + u * a.N + my_v] = __uint_as_float(r[i >> 4][i & 15]);
@@ -366,18 +371,24 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
                 }
             }
         }
-        if (a.J > 1) {                                             // (N1MAX = 32: r[0] was column group 0, r[1] group 1)
+        if (a.J == 4) {                                            // (N1MAX = 32, Ms = 8: one map per 8 columns)
             red[wtid] = e0;
-            red[128 + wtid] = e1;
+            red[128 + wtid] = f0;
+            red[256 + wtid] = e1;
+            red[384 + wtid] = f1;
+        } else if (a.J == 2) {                                     // (Ms = 16: r[0] was map column 0, r[1] map column 1)
+            red[wtid] = e0 + f0;
+            red[128 + wtid] = e1 + f1;
         } else {
-            red[wtid] = e0 + e1;
+            red[wtid] = (e0 + f0) + (e1 + f1);
         }
         named_bar_sync(bar_id, TPS);
         {
             // TPM threads per map, fixed summation order -> bit-reproducible per-map energy
             float s = 0.f;
-            if (red_sub < (uint32_t)a.N) s = red_row[red_sub];
-            if (red_sub + tpm < (uint32_t)a.N) s += red_row[red_sub + tpm];      // N <= 2 * TPM for every shape routed here
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)                       // N <= 4 * TPM for every shape routed here
+                if (red_sub + k * tpm < (uint32_t)a.N) s += red_row[red_sub + k * tpm];
 #pragma unroll
             for (uint32_t o = 16; o > 0; o >>= 1)
                 if (o < tpm) s += __shfl_xor_sync(0xffffffffu, s, o);

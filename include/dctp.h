@@ -40,7 +40,7 @@ extern "C" {
 #define DCTP_PATH_AUTO   0        /* the fastest tensor-core kernel the shape allows, CUDA cores otherwise */
 #define DCTP_PATH_UMMA   1        /* tcgen05/TMEM bf16x3 kernel, operands in shared memory; square maps, side <= 128, contiguous maps */
 #define DCTP_PATH_SIMT   2        /* fp32 CUDA-core kernels; any H x W, strided rows */
-#define DCTP_PATH_TMEM   3        /* tcgen05 kernel with TMEM-resident operands; dense square maps, even side 10..64 */
+#define DCTP_PATH_TMEM   3        /* tcgen05 kernel with TMEM-resident operands; dense square maps, side 5..64 (odd sides up to 13) */
 #define DCTP_PATH_LARGE  4        /* tiled tcgen05 kernel; dense square maps, side 80..320, side % 16 == 0 (AUTO: from 96) */
 
 int dctp_version(void);
