@@ -16,14 +16,17 @@ dev = torch.device('cuda', 0)
 lib = _lib.load()
 _lib.check(lib.dctp_init())
 x = torch.relu(torch.randn(B, C, H, W, device=dev))
+# rotate through enough copies that no launch finds its input in the 126 MB L2 (a single re-used tensor below that size
+# measures L2, not HBM - it made 7x7 look 35 % faster on one kernel than it is inside a real step)
+copies = [x] + [x.clone() for _ in range(max(0, int(400e6 // (x.numel() * 4))))]
 acc = torch.zeros(C, dtype=torch.float64, device=dev)
 for _ in range(2):
     dct_energy(x, path=path, accum=acc, check=False)
 torch.cuda.synchronize()
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0.record()
-for _ in range(iters):
-    dct_energy(x, path=path, accum=acc, check=False)
+for i in range(iters):
+    dct_energy(copies[i % len(copies)], path=path, accum=acc, check=False)
 t1.record()
 torch.cuda.synchronize()
 ms = t0.elapsed_time(t1) / iters
