@@ -399,8 +399,9 @@ bool t_shape_ok(int N) {
 // odd sides: a float4 of the stream may straddle maps, the stream itself must not end inside one
 bool t_stream_ok(int N, long long n_maps) { return (N % 2) == 0 || (n_maps * N * N) % 4 == 0; }
 bool t_launch_ok(int N, long long bytes) {
-    // (sides <= 8, four maps side by side per slot, are supported but not routed: inside ResNet-50's step, with the input coming
-    //  from HBM rather than a warm L2, [256,2048,7,7] takes 69 us with either kernel)
+    // (sides <= 8, four maps side by side per slot, are supported but not routed: back to back on one shape this kernel shows
+    //  [256,2048,7,7] at 2.09 vs 1.48 TB/s because its longer prologue hides behind the previous launch, but inside ResNet-50's
+    //  step the launch takes 69 us with either kernel and the step is not faster)
     return t_shape_ok(N) && (g.t_all || N >= g.t_auto_lo || (N >= 10 && bytes >= g.t_min_bytes));
 }
 
