@@ -53,18 +53,20 @@ class Selection:
     conv: str      # state_dict name of the conv whose filters are gathered
 
 
-def _shapes(net_name, rates):
+def _shapes(net_name, rates, origin_rates=None):
     from .zoo import get_network
     with torch.device('meta'):
-        orig = get_network(net_name, [0.] * 100)
+        orig = get_network(net_name, [0.] * 100 if origin_rates is None else list(origin_rates))
         pruned = get_network(net_name, list(rates))
     ow = {n: m.weight.shape for n, m in orig.named_modules() if isinstance(m, nn.Conv2d)}
     pw = {n: m.weight.shape for n, m in pruned.named_modules() if isinstance(m, nn.Conv2d)}
     return orig, pruned, ow, pw
 
 
-def selection_plan(net_name, rates) -> List[Selection]:
-    orig, pruned, ow, pw = _shapes(net_name, rates)
+def selection_plan(net_name, rates, origin_rates=None) -> List[Selection]:
+    """The selections the reference's loader for `net_name` performs when it fills the net built with `rates` from the
+    net built with `origin_rates` (None: the unpruned net; a list: an already pruned one, prune_dynamic.py:150-154)."""
+    orig, pruned, ow, pw = _shapes(net_name, rates, origin_rates)
     plan = []
 
     def consider(conv, stem, even_if_full=False):

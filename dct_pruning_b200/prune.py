@@ -15,13 +15,15 @@ from .zoo import get_network
 
 
 def pruned_model(net_name, compress_rate, origin_model, limit=5, batch_size=128, loader=None, scores=None,
-                 input_side=None, seed=None, out_root=None):
+                 input_side=None, seed=None, out_root=None, origin_rates=None):
     """Returns (pruned net on origin_model's device, {file stem: score vector}, [(Selection, kept ids)]).
 
     compress_rate: the reference's string form (`'[0.]+[0.18]*29'`) or a list of floats.  `scores` skips the scoring
     pass (e.g. files of an earlier run: a directory or a {stem: vector} mapping).  `seed` seeds the pruned net's own
     initialisation - the tensors the loaders do not fill (biases, most BatchNorms, the classifier of VGG) keep it, as in
-    the reference.  `out_root` additionally writes the reference's importance_score/<net>_limit<N>/*.npy files."""
+    the reference.  `out_root` additionally writes the reference's importance_score/<net>_limit<N>/*.npy files.
+    `origin_rates`: the rates `origin_model` was built with when it is itself a pruned net - one round of
+    prune_dynamic.py's loop (score the fine-tuned pruned net, prune it further)."""
     device = next(origin_model.parameters()).device
     if device.type != 'cuda':
         raise RuntimeError('pruned_model needs the unpruned net on a CUDA device (got %s); there is no CPU fallback' % device)
@@ -29,9 +31,9 @@ def pruned_model(net_name, compress_rate, origin_model, limit=5, batch_size=128,
     if scores is None:
         args = types.SimpleNamespace(net=net_name, limit=limit, batch_size=batch_size, input_side=input_side)
         scores = imp_score(origin_model, args, loader=loader, out_root=out_root or 'importance_score', write=out_root is not None)
-    kept = kept_channels(net_name, rates, scores, device=device)
+    kept = kept_channels(net_name, rates, scores, device=device, origin_rates=origin_rates)
     if seed is not None:
         torch.manual_seed(seed)
     net = get_network(net_name, rates).to(device).eval()
-    transfer_weights(net_name, net, origin_model.state_dict(), kept)
+    transfer_weights(net_name, net, origin_model.state_dict(), kept, origin_rates=origin_rates)
     return net, scores, kept

@@ -45,12 +45,13 @@ def select_index(imp, k, device='cuda'):
     return topk_segmented(t, [0, t.numel()], [k])[0].cpu().numpy()
 
 
-def kept_channels(net_name, compress_rate, scores, device='cuda'):
+def kept_channels(net_name, compress_rate, scores, device='cuda', origin_rates=None):
     """For every selection the reference's loader for `net_name` performs under `compress_rate`
     (string or list of floats), the kept channel ids.  `scores` maps file stem -> vector (numpy or
-    tensor) or is a directory holding the .npy files.  Returns [(Selection, int64 numpy array)]."""
+    tensor) or is a directory holding the .npy files.  `origin_rates`: the rates of the scored net when it is itself a
+    pruned one (iterative pruning).  Returns [(Selection, int64 numpy array)]."""
     rates = get_compress_rate(compress_rate) if isinstance(compress_rate, str) else list(compress_rate)
-    plan = selection_plan(net_name, rates)
+    plan = selection_plan(net_name, rates, origin_rates)
     if isinstance(scores, str):
         import os
         scores = {s.stem: np.load(os.path.join(scores, s.stem + '.npy')) for s in plan}

@@ -50,9 +50,10 @@ def _convs_and_linears(model):
     return convs, linears
 
 
-def transfer_plan(net_name, pruned_model, ori_shapes):
+def transfer_plan(net_name, pruned_model, ori_shapes, origin_rates=None):
     """The ops that turn the original state dict into the pruned model's, in the reference's order.
-    `ori_shapes`: {state-dict key: shape} of the unpruned net."""
+    `ori_shapes`: {state-dict key: shape} of the net the weights come from; `origin_rates`: its compress rates when it is
+    itself a pruned net (only GoogLeNet's loader takes them: its `cpr` argument, used by prune_dynamic.py:154)."""
     new_shapes = {k: tuple(v.shape) for k, v in pruned_model.state_dict().items()}
     convs, linears = _convs_and_linears(pruned_model)
     ops = []
@@ -169,6 +170,10 @@ def transfer_plan(net_name, pruned_model, ori_shapes):
     if net_name == 'googlenet':                                  # load_models.py:146-380 (cpr=None, as load_model calls it)
         filters = [[64, 128, 32, 32], [128, 192, 96, 64], [192, 208, 48, 64], [160, 224, 64, 64], [128, 256, 64, 64],
                    [112, 288, 64, 64], [256, 320, 128, 128], [256, 320, 128, 128], [384, 384, 128, 128]]
+        if origin_rates is not None:                             # :160-163: the source net's own branch widths
+            for i, f in enumerate(filters):
+                f[1] = int(f[1] * (1 - origin_rates[i + 1]))
+                f[2] = int(f[2] * (1 - origin_rates[i + 1]))
         listed_convs, listed_bns = set(), set()
         cur_last, cnt = [], 0
 
@@ -375,7 +380,7 @@ def apply_plan(plan, ori_state, new_state, kept, gather=gather_weight):
     return new_state
 
 
-def transfer_weights(net_name, pruned_model, ori_state, kept, check=True):
+def transfer_weights(net_name, pruned_model, ori_state, kept, check=True, origin_rates=None):
     """Fill `pruned_model` (on a CUDA device) from the unpruned `ori_state` with the kept channels of every pruned
     layer; `kept` as returned by `topk.kept_channels` ([(Selection, ids)]) or a {stem: ids} mapping."""
     device = next(pruned_model.parameters()).device
@@ -385,7 +390,7 @@ def transfer_weights(net_name, pruned_model, ori_state, kept, check=True):
         kept = {sel.stem: ids for sel, ids in kept}
     kept = {k: torch.as_tensor(v, dtype=torch.int64).to(device) for k, v in kept.items()}
     ori = {k: v.to(device) for k, v in ori_state.items()}
-    plan = transfer_plan(net_name, pruned_model, {k: tuple(v.shape) for k, v in ori.items()})
+    plan = transfer_plan(net_name, pruned_model, {k: tuple(v.shape) for k, v in ori.items()}, origin_rates)
     state = apply_plan(plan, ori, dict(pruned_model.state_dict()), kept)
     if check:
         _lib.check(_lib.load().dctp_check(_lib.current_stream()))

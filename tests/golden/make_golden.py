@@ -335,6 +335,62 @@ def gen_transfer(common, load_models, only=None):
         print('transfer', net_name, len(after), 'tensors,', len(changed), 'changed by the loader')
 
 
+def gen_transfer_iter(common, load_models):
+    """One round of prune_dynamic.py:150-154 for GoogLeNet: score the net pruned at 1/5 of the README rate, then let the
+    reference loader (with its `cpr` argument = the rates of that already pruned net) fill the net pruned at 2/5."""
+    final = common.get_compress_rate(types.SimpleNamespace(compress_rate='[0.4]+[0.85]*2+[0.9]*5+[0.9]*2'))
+    rate_a, rate_b = list(np.array(final) / 5), list((np.array(final) / 5) * 2)
+    net_a = build_net(common, 'googlenet', rate_a)
+    net_b = build_net(common, 'googlenet', rate_b)
+    before = tensor_digests(net_b.state_dict())
+    scores = run_imp_score(common, 'googlenet', net_a, 2, 32, 1)
+    calls = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for k, v in scores.items():
+            np.save(os.path.join(tmp, k + '.npy'), v)
+
+        class NpProxy:
+            def __getattr__(self, k):
+                return getattr(np, k)
+
+            @staticmethod
+            def load(path):
+                arr = np.load(path)
+                calls.append({'file': os.path.basename(path)[:-4], 'C': int(arr.shape[0])})
+                return arr
+
+            @staticmethod
+            def argsort(a, *args, **kw):
+                res = np.argsort(a, *args, **kw)
+
+                class Tap(np.ndarray):
+                    def __getitem__(self, item):
+                        got = np.asarray(self).__getitem__(item)
+                        if isinstance(item, slice) and 'k' not in calls[-1]:
+                            calls[-1]['k'] = int(len(got))
+                            calls[-1]['select_index'] = sorted(int(v) for v in got)
+                        return got
+                return res.view(Tap)
+        load_models.np = NpProxy()
+        try:
+            load_models.load_google_model(net_b, net_a.state_dict(), types.SimpleNamespace(imp_score=tmp, net='googlenet'), rate_a)
+        finally:
+            load_models.np = np
+    after = tensor_digests(net_b.state_dict())
+    h = hashlib.sha256()
+    for k in before:
+        h.update(k.encode())
+        h.update(before[k][2].encode())
+    changed = {k: after[k] for k in after if after[k][2] != before[k][2]}
+    same = hashlib.sha256(''.join(k + after[k][2] for k in after if after[k][2] == before[k][2]).encode()).hexdigest()
+    np.savez_compressed(os.path.join(HERE, 'scores_googlenet_iter_b2_l1.npz'), **scores)
+    with open(os.path.join(HERE, 'transfer_googlenet_iter.json'), 'w') as f:
+        json.dump({'net': 'googlenet', 'origin_rates': rate_a, 'rates': rate_b, 'scores': 'googlenet_iter_b2_l1',
+                   'pruned_init_digest': h.hexdigest(), 'n_tensors': len(after), 'changed': changed, 'unchanged_digest': same,
+                   'selections': calls}, f)
+    print('transfer_iter googlenet', len(after), 'tensors,', len(changed), 'changed,', len(calls), 'selections')
+
+
 # ----------------------------------------------------------------------- shipped
 def gen_shipped():
     out = {}
@@ -365,5 +421,7 @@ if __name__ == '__main__':
         gen_topk(common, load_models)
     if what in ('all', 'transfer'):
         gen_transfer(common, load_models, only)
+    if what in ('all', 'transfer_iter'):
+        gen_transfer_iter(common, load_models)
     if what in ('all', 'shipped'):
         gen_shipped()

@@ -161,3 +161,43 @@ def test_score_select_rebuild_fill_on_device(lib, cuda_device):
     with torch.no_grad():
         y = net(torch.randn(2, 3, 32, 32, device=cuda_device))
     assert y.shape == (2, 10) and torch.isfinite(y).all()
+
+
+def load_iter_case():
+    with open(os.path.join(GOLDEN, 'transfer_googlenet_iter.json')) as f:
+        gold = json.load(f)
+    kept = {s['file']: np.asarray(s['select_index'], dtype=np.int64) for s in gold['selections'] if 'select_index' in s}
+    torch.manual_seed(0)
+    net_a = get_network('googlenet', gold['origin_rates']).eval()
+    torch.manual_seed(0)
+    net_b = get_network('googlenet', gold['rates']).eval()
+    return gold, kept, net_a, net_b
+
+
+def test_iterative_round_reproduces_reference_loader():
+    """prune_dynamic.py:150-154: the source net is itself pruned; GoogLeNet's loader then takes the source's rates (`cpr`)."""
+    from dct_pruning_b200.compress import selection_plan
+    gold, kept, net_a, net_b = load_iter_case()
+    before = digests(net_b.state_dict())
+    assert init_digest(before) == gold['pruned_init_digest']
+    plan_sel = selection_plan('googlenet', gold['rates'], gold['origin_rates'])
+    want = [(s['file'], s['C'], s['k']) for s in gold['selections']]
+    assert [(s.stem, s.C, s.k) for s in plan_sel] == want
+    ori = {k: v.clone() for k, v in net_a.state_dict().items()}
+    plan = transfer.transfer_plan('googlenet', net_b, {k: tuple(v.shape) for k, v in ori.items()}, origin_rates=gold['origin_rates'])
+    state = transfer.apply_plan(plan, ori, dict(net_b.state_dict()), kept, gather=cpu_gather)
+    net_b.load_state_dict(state)
+    check_against_golden(gold, before, digests(net_b.state_dict()))
+
+
+@pytest.mark.gpu
+def test_iterative_round_on_device(lib, cuda_device):
+    from dct_pruning_b200.prune import pruned_model
+    gold, kept_ref, net_a, net_b = load_iter_case()
+    before = digests(net_b.state_dict())
+    scores = np.load(os.path.join(GOLDEN, 'scores_%s.npz' % gold['scores']))
+    scores = {k: scores[k] for k in scores.files}
+    net, _, kept = pruned_model('googlenet', gold['rates'], net_a.to(cuda_device), scores=scores, seed=0, origin_rates=gold['origin_rates'])
+    if all(np.array_equal(ids, kept_ref[sel.stem]) for sel, ids in kept):       # (no tie fell on a cut: same selections as the reference)
+        check_against_golden(gold, before, digests(net.state_dict()))
+    assert len(kept) == len(gold['selections'])
