@@ -391,6 +391,79 @@ def gen_transfer_iter(common, load_models):
     print('transfer_iter googlenet', len(after), 'tensors,', len(changed), 'changed,', len(calls), 'selections')
 
 
+TRANSFER_ALT_CASES = [  # a second compress rate per net (README.md's other settings): different k patterns, same scores
+    ('vgg_16_bn', 'vgg_16_bn_b3_l2', '[0.30]*7+[0.75]*5'),
+    ('resnet_56', 'resnet_56_b2_l2', '[0.]+[0.4]*2+[0.5]*9+[0.6]*9+[0.7]*9'),
+    ('resnet_110', 'resnet_110_b1_l1', '[0.]+[0.4]*2+[0.5]*18+[0.65]*36'),
+    ('densenet_40', 'densenet_40_b2_l1', '[0.]+[0.4]*12+[0.]+[0.4]*12+[0.]+[0.4]*12'),
+    ('googlenet', 'googlenet_b2_l1', '[0.3]+[0.6]*2+[0.7]*5+[0.8]*2'),
+    ('resnet_50', 'resnet_50_s64_b2_l1', '[0.]+[0.2]*3+[0.65]*16'),
+    ('u2netp', 'u2netp_s64_b1_l2', '[0.20]*40'),
+]
+
+
+def gen_transfer_alt(common, load_models, only=None):
+    loaders = {'vgg_16_bn': lambda m, od, a: load_models.load_vgg_model(m, od, a),
+               'resnet_56': lambda m, od, a: load_models.load_resnet_model(m, od, 56, a),
+               'resnet_110': lambda m, od, a: load_models.load_resnet_model(m, od, 110, a),
+               'densenet_40': lambda m, od, a: load_models.load_densenet_model(m, od, a),
+               'googlenet': lambda m, od, a: load_models.load_google_model(m, od, a),
+               'resnet_50': lambda m, od, a: load_models.load_resnet_imagenet_model(m, od, a),
+               'u2netp': lambda m, od, a: load_models.load_u2netp_model(m, od, a)}
+    for net_name, score_tag, rate_str in TRANSFER_ALT_CASES:
+        if only and only != net_name:
+            continue
+        rate = common.get_compress_rate(types.SimpleNamespace(compress_rate=rate_str))
+        orig = build_net(common, net_name)
+        pruned = build_net(common, net_name, rate)
+        before = tensor_digests(pruned.state_dict())
+        scores = np.load(os.path.join(HERE, 'scores_%s.npz' % score_tag))
+        calls = []
+        with tempfile.TemporaryDirectory() as tmp:
+            for k in scores.files:
+                if k != '__meta__':
+                    np.save(os.path.join(tmp, k + '.npy'), scores[k])
+
+            class NpProxy:
+                def __getattr__(self, k):
+                    return getattr(np, k)
+
+                @staticmethod
+                def load(path):
+                    arr = np.load(path)
+                    calls.append({'file': os.path.basename(path)[:-4], 'C': int(arr.shape[0])})
+                    return arr
+
+                @staticmethod
+                def argsort(a, *args, **kw):
+                    res = np.argsort(a, *args, **kw)
+
+                    class Tap(np.ndarray):
+                        def __getitem__(self, item):
+                            got = np.asarray(self).__getitem__(item)
+                            if isinstance(item, slice) and 'k' not in calls[-1]:
+                                calls[-1]['k'] = int(len(got))
+                                calls[-1]['select_index'] = sorted(int(v) for v in got)
+                            return got
+                    return res.view(Tap)
+            load_models.np = NpProxy()
+            try:
+                loaders[net_name](pruned, orig.state_dict(), types.SimpleNamespace(imp_score=tmp, net=net_name))
+            finally:
+                load_models.np = np
+        after = tensor_digests(pruned.state_dict())
+        h = hashlib.sha256()
+        for k in before:
+            h.update(k.encode())
+            h.update(before[k][2].encode())
+        changed = {k: after[k] for k in after if after[k][2] != before[k][2]}
+        same = hashlib.sha256(''.join(k + after[k][2] for k in after if after[k][2] == before[k][2]).encode()).hexdigest()
+        with open(os.path.join(HERE, 'transfer_%s_alt.json' % net_name), 'w') as f:
+            json.dump({'net': net_name, 'scores': score_tag, 'compress_rate': rate_str, 'pruned_init_digest': h.hexdigest(),
+                       'n_tensors': len(after), 'changed': changed, 'unchanged_digest': same, 'selections': calls}, f)
+        print('transfer_alt', net_name, len(after), 'tensors,', len(changed), 'changed,', len(calls), 'selections')
+
+
 # ----------------------------------------------------------------------- shipped
 def gen_shipped():
     out = {}
@@ -423,5 +496,7 @@ if __name__ == '__main__':
         gen_transfer(common, load_models, only)
     if what in ('all', 'transfer_iter'):
         gen_transfer_iter(common, load_models)
+    if what in ('all', 'transfer_alt'):
+        gen_transfer_alt(common, load_models, only)
     if what in ('all', 'shipped'):
         gen_shipped()

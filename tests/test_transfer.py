@@ -201,3 +201,24 @@ def test_iterative_round_on_device(lib, cuda_device):
     if all(np.array_equal(ids, kept_ref[sel.stem]) for sel, ids in kept):       # (no tie fell on a cut: same selections as the reference)
         check_against_golden(gold, before, digests(net.state_dict()))
     assert len(kept) == len(gold['selections'])
+
+
+@pytest.mark.parametrize('net', transfer.SUPPORTED)
+def test_plan_reproduces_reference_loader_second_rate(net):
+    """A second compress rate per net (other k patterns), selections captured from the reference loader's own argsort calls."""
+    from dct_pruning_b200.compress import selection_plan
+    with open(os.path.join(GOLDEN, 'transfer_%s_alt.json' % net)) as f:
+        gold = json.load(f)
+    kept = {s['file']: np.asarray(s['select_index'], dtype=np.int64) for s in gold['selections'] if 'select_index' in s}
+    rates = get_compress_rate(gold['compress_rate'])
+    assert [(s.stem, s.C, s.k) for s in selection_plan(net, rates)] == [(s['file'], s['C'], s['k']) for s in gold['selections']]
+    torch.manual_seed(0)
+    orig = get_network(net).eval()
+    torch.manual_seed(0)
+    pruned = get_network(net, rates).eval()
+    before = digests(pruned.state_dict())
+    assert init_digest(before) == gold['pruned_init_digest']
+    ori = {k: v.clone() for k, v in orig.state_dict().items()}
+    plan = transfer.transfer_plan(net, pruned, {k: tuple(v.shape) for k, v in ori.items()})
+    pruned.load_state_dict(transfer.apply_plan(plan, ori, dict(pruned.state_dict()), kept, gather=cpu_gather))
+    check_against_golden(gold, before, digests(pruned.state_dict()))
