@@ -64,7 +64,8 @@ def parse():
     p.add_argument('--impl', default='ours', choices=('ours', 'reference'))
     p.add_argument('--net', default='resnet_50', choices=tuple(WORKLOADS))
     p.add_argument('--batch', type=int, default=None)
-    p.add_argument('--path', default='auto', choices=('auto', 'umma', 'simt'))
+    p.add_argument('--path', default='auto', choices=('auto', 'umma', 'simt'),
+                   help="kernel path of the hook launches (the whole net must fit a forced path, so 'tmem' / 'large' are left to 'auto')")
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--graph', action='store_true', help='replay CUDA graphs (hook launches of a step; forward + hooks in the e2e leg): takes the host out of launch-bound nets')
