@@ -239,6 +239,8 @@ def run_ours(args):
             return 'score_simt_kernel (fp32 CUDA cores)'
         if n > 64:
             return 'score_umma_kernel<128> (tcgen05, smem operands)'
+        if n in (52, 56):
+            return 'score_t_kernel<64,3> (tcgen05, TMEM-resident operands, 2 producer warpgroups)'
         if n % 2 == 0 and 52 <= n <= 64:
             return 'score_t_kernel<64,3> (tcgen05, TMEM-resident operands, register prefetch)'
         if n % 2 == 0 and 10 <= n <= 32 and a.numel() * 4 >= (32 << 20):

@@ -64,6 +64,8 @@ struct State {
     std::map<int, LargeBasis> large;                   // N
     int t_slots = 3;                                   // tile slots per CTA of the TMEM-operand kernel (DCTP_T_SLOTS=0 disables it)
     bool t_all = false;
+    bool t_prod = true;                                // 3-slot TMEM-operand kernel with two producer warpgroups where the tile fits
+                                                       // (52x52, 56x56; DCTP_TP=0 turns it off): ResNet-50 step 3.30 -> 3.15 ms
     bool pdl = true;                                   // programmatic dependent launch of the score kernels (DCTP_PDL=0 disables)
     int t_auto_lo = 52;                                // sides from here up always go to the TMEM-operand kernel under AUTO (DCTP_T_LO)
     int large_lo = 96;                                 // smallest side AUTO routes to the tiled large-map kernel (DCTP_LARGE_LO);
@@ -302,12 +304,14 @@ int ensure_init() {
     {
         const void* fns[] = {reinterpret_cast<const void*>(score_t_kernel<64, 3, 1>), reinterpret_cast<const void*>(score_t_kernel<64, 3, 2>),
                              reinterpret_cast<const void*>(score_t_kernel<32, 6, 1>), reinterpret_cast<const void*>(score_t_kernel<32, 6, 2>),
-                             reinterpret_cast<const void*>(score_t_kernel<32, 6, 4>)};
+                             reinterpret_cast<const void*>(score_t_kernel<32, 6, 4>),
+                             reinterpret_cast<const void*>(score_t_kernel<64, 3, 1, 2>), reinterpret_cast<const void*>(score_t_kernel<64, 3, 2, 2>)};
         for (const void* fn : fns) {
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
     }
+    if (const char* e = std::getenv("DCTP_TP")) g.t_prod = std::atoi(e) != 0;
     if (const char* e = std::getenv("DCTP_PDL")) g.pdl = std::atoi(e) != 0;
     if (const char* e = std::getenv("DCTP_LARGE_LO")) g.large_lo = std::atoi(e);
     if (const char* e = std::getenv("DCTP_T_MIN_MB")) g.t_min_bytes = static_cast<long long>(std::atoi(e)) << 20;
@@ -444,7 +448,12 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
     if (grid > need) grid = need;
     a.chan_step = static_cast<int>((static_cast<long long>(grid) * ns * a.MT) % c_count);
     const bool v2 = basis.vpe == 2;
-    if (n1max == 64) {
+    if (n1max == 64 && g.t_prod && basis.tile_vec <= 13 * 128 && !v2) {   // producer warpgroups: tiles of at most 13 float4 per thread
+                                                                          // (and the 2-byte scatter table: 52x52, 56x56 fit in shared memory)
+        const size_t smem_p = TScoreSmem<64, 2>::total(ns, a.scatter_bytes);
+        if (v2) CUDA_TRY(launch_score(score_t_kernel<64, 3, 2, 2>, grid, 640, smem_p, stream, a));
+        else CUDA_TRY(launch_score(score_t_kernel<64, 3, 1, 2>, grid, 640, smem_p, stream, a));
+    } else if (n1max == 64) {
         if (v2) CUDA_TRY(launch_score(score_t_kernel<64, 3, 2>, grid, 384, smem, stream, a));
         else CUDA_TRY(launch_score(score_t_kernel<64, 3, 1>, grid, 384, smem, stream, a));
     } else {

@@ -78,7 +78,7 @@ struct TScoreArgs {
     FastDiv div_ms;
 };
 
-template <int N1MAX>
+template <int N1MAX, int NPROD = 0>
 struct TScoreSmem {
     static constexpr uint32_t BX_HALF = 2 * N1MAX * 128;           // data operand (hi or lo): 2 K-blocks x N1MAX rows x 128 B
     static constexpr uint32_t SLOT_BYTES = 2 * BX_HALF;
@@ -88,8 +88,12 @@ struct TScoreSmem {
     static constexpr bool STAGED = N1MAX < 64;
     static constexpr uint32_t PF = N1MAX == 64 ? 16 : 8;                       // float4 of a tile per thread
     static constexpr uint32_t STAGE_BYTES = STAGED ? PF * 128 * 16 : 0;        // per slot: fp32 tile, thread-private vectors
+    // producer variant (NPROD extra warpgroups convert for all slots): per producer two fp32 tiles in flight, 13 float4 per thread each
+    static constexpr uint32_t PPF = 13, PSTAGE_BYTES = PPF * 128 * 16;
     __host__ __device__ static constexpr uint32_t off_stage(int nslot) { return nslot * SLOT_BYTES; }
-    __host__ __device__ static constexpr uint32_t off_c(int nslot) { return nslot * (SLOT_BYTES + STAGE_BYTES); }
+    __host__ __device__ static constexpr uint32_t off_c(int nslot) {
+        return nslot * (SLOT_BYTES + STAGE_BYTES) + NPROD * 2 * PSTAGE_BYTES;
+    }
     __host__ __device__ static constexpr uint32_t off_ctrl(int nslot) { return off_c(nslot) + 2 * C_HALF; }
     __host__ __device__ static constexpr uint32_t off_red(int nslot) { return off_ctrl(nslot) + 128; }
     __host__ __device__ static constexpr uint32_t off_table(int nslot) { return off_red(nslot) + nslot * 2048; }   // 4 x 128 floats per slot
@@ -100,14 +104,17 @@ struct TScoreSmem {
 
 // N1MAX: widest accumulator a slot holds (64 / 32 columns); NSLOT tile slots per CTA (one warpgroup each);
 // VPE: scatter pieces per float4 (1: N % 4 == 0, one 8-byte store; 2: N even, two 4-byte stores; 4: N odd, four 2-byte stores)
-template <int N1MAX, int NSLOT, int VPE>
-__global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArgs a) {
-    using S = TScoreSmem<N1MAX>;
+// NPROD: 0 = every slot's warpgroup loads and converts its own tiles; 2 = two extra producer warpgroups load (cp.async, two tiles
+// each in flight) and convert for all slots, so a slot's chain is only MMA / epilogue / MMA / epilogue (tiles of <= 1664 float4)
+template <int N1MAX, int NSLOT, int VPE, int NPROD = 0>
+__global__ void __launch_bounds__(128 * (NSLOT + NPROD), 1) score_t_kernel(const TScoreArgs a) {
+    using S = TScoreSmem<N1MAX, NPROD>;
     using namespace umma;
     constexpr int WPS = 4, TPS = 128;                              // one warpgroup (= all 128 TMEM lanes) per slot
-    constexpr int NT = TPS * NSLOT;
+    constexpr int NT = TPS * (NSLOT + NPROD);
     constexpr int TSCORE_PF = S::PF;                               // float4 per thread: a full tile
     constexpr bool STAGED = S::STAGED;
+    static_assert(NPROD == 0 || !STAGED, "the producer variant is for the 3-slot kernel");
     constexpr uint32_t SLOT_COLS = 2 * N1MAX;
     constexpr uint32_t TMEM_COLS = 512;
     static_assert(128 + NSLOT * SLOT_COLS <= TMEM_COLS, "TMEM budget");
@@ -122,10 +129,14 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     uint8_t* c_hi = smem + S::off_c(NSLOT);
     uint8_t* c_lo = c_hi + S::C_HALF;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_ctrl(NSLOT));
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_ctrl(NSLOT) + 64);
-    float* red = reinterpret_cast<float*>(smem + S::off_red(NSLOT)) + wg * 512;      // [map column j][lane]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::off_ctrl(NSLOT) + 112);
+    [[maybe_unused]] uint64_t* full = bars + NSLOT;                // (NPROD) a slot's data operand has been written
+    [[maybe_unused]] uint64_t* bxfree = bars + 2 * NSLOT;          // (NPROD) [slot][producer]: the MMAs that read it are done, signalled
+                                                                   //         to the producer that writes the slot next (each barrier has one waiter
+                                                                   //         that sees every phase: a waiter skipping phases would mis-read parity)
+    float* red = reinterpret_cast<float*>(smem + S::off_red(NSLOT)) + (wg < NSLOT ? wg : 0) * 512;      // [map column j][lane]
     const Entry* scat = reinterpret_cast<const Entry*>(smem + S::off_table(NSLOT));
-    uint64_t* bar = bars + wg;
+    uint64_t* bar = bars + (wg < NSLOT ? wg : 0);
 
     if ((smem_u32(smem) & 1023u) != 0) {
         if (tid == 0) atomicExch(a.status, DCTP_DEV_SMEM_ALIGN);
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     const int first = blockIdx.x * NSLOT + (int)wg, stride = gridDim.x * NSLOT;
 
     // ---- register prefetch of a tile
-    [[maybe_unused]] float4 pf[STAGED ? 1 : TSCORE_PF];
+    [[maybe_unused]] float4 pf[(STAGED || NPROD > 0) ? 1 : TSCORE_PF];
     uint32_t pf_full = 0;
     float4* stage = reinterpret_cast<float4*>(smem + S::off_stage(NSLOT) + wg * S::STAGE_BYTES) + wtid;   // (STAGED)
     auto prefetch = [&](int tile) {
@@ -149,7 +160,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
             for (int u = 0; u < TSCORE_PF; ++u)
                 if (wtid + u * TPS < pf_full) cp_async16(dst + u * TPS * 16, src + u * TPS);
             cp_async_commit();
-        } else {
+        } else if constexpr (NPROD == 0) {
 #pragma unroll
             for (int u = 0; u < TSCORE_PF; ++u)
                 if (wtid + u * TPS < pf_full) pf[u] = detail::ldg_stream(src + u * TPS);
@@ -172,6 +183,10 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
     if (tid == 0) {
         for (int s = 0; s < NSLOT; ++s) mbar_init(bars + s, 1);
+        if constexpr (NPROD > 0) {
+            for (int s = 0; s < NSLOT; ++s) mbar_init(full + s, TPS);
+            for (int s = 0; s < NSLOT * NPROD; ++s) mbar_init(bxfree + s, 1);
+        }
         mbar_init_fence();
     }
     fence_async_smem();
@@ -200,7 +215,60 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
 
     launch_dependents();                                           // only now: this CTA holds its TMEM columns (see score_umma.cuh)
     grid_dependency_wait();                                        // the activation (written by the preceding kernel) is complete
-    if (first < a.num_tiles) prefetch(first);
+    bool alive = true;
+    if constexpr (NPROD > 0) {
+        if (wg >= (uint32_t)NSLOT) {
+            // ===================================================== producer warpgroup: load + convert for every slot of the CTA
+            // The CTA's tiles in the order q = 0, 1, 2, ...: slot q % NSLOT, tile (blockIdx.x * NSLOT + slot) + (q / NSLOT) * stride;
+            // producer pw takes q = pw, pw + NPROD, ...  Two tiles per producer are in flight as cp.async copies (thread-private
+            // staging: each thread later converts exactly the vectors it requested, so no barrier guards the staging buffers).
+            const uint32_t pw = wg - NSLOT;
+            float4* pst = reinterpret_cast<float4*>(smem + S::off_stage(NSLOT) + pw * 2 * S::PSTAGE_BYTES) + wtid;
+            auto tile_of = [&](uint32_t q) { return (int)(blockIdx.x * NSLOT + q % NSLOT) + (int)(q / NSLOT) * stride; };
+            auto vectors_of = [&](int tile) {
+                const long long elem0 = static_cast<long long>(tile) * a.MT * a.NN;
+                return static_cast<uint32_t>(min(static_cast<long long>(a.tile_vec), (a.total_elems - elem0) >> 2));
+            };
+            auto request = [&](uint32_t q, uint32_t buf) {
+                const int tile = tile_of(q);
+                if (tile < a.num_tiles) {
+                    const uint32_t n = vectors_of(tile);
+                    const float4* src = reinterpret_cast<const float4*>(a.x_dense + static_cast<long long>(tile) * a.MT * a.NN) + wtid;
+                    const uint32_t dst = smem_u32(pst) + buf * S::PSTAGE_BYTES;
+#pragma unroll
+                    for (uint32_t u = 0; u < S::PPF; ++u)
+                        if (wtid + u * TPS < n) cp_async16(dst + u * TPS * 16, src + u * TPS);
+                }
+                cp_async_commit();
+            };
+            uint32_t q = pw, seen = 0;                             // seen: parity of the next bxfree phase to wait for, one bit per slot
+            request(q, 0);
+            request(q + NPROD, 1);
+            for (uint32_t k = 0;; ++k, q += NPROD) {
+                const int tile = tile_of(q);
+                if (tile >= a.num_tiles) break;
+                cp_async_wait_but_one();
+                const uint32_t slot = q % NSLOT, fill = q / NSLOT;
+                if (fill >= 1) {                                   // stage-1 MMAs of the slot's previous tile are done
+                    if (alive && !mbar_wait(bxfree + slot * NPROD + pw, (seen >> slot) & 1u)) alive = false;
+                    seen ^= 1u << slot;
+                }
+                uint8_t* hi = smem + slot * S::SLOT_BYTES;
+                uint8_t* lo = hi + S::BX_HALF;
+                const uint32_t n = vectors_of(tile);
+                const float4* stg = pst + (k & 1u) * (S::PSTAGE_BYTES / 16);
+#pragma unroll
+                for (uint32_t u = 0; u < S::PPF; ++u)
+                    if (wtid + u * TPS < n) detail::Scatter<VPE>::st(hi, lo, scat[wtid + u * TPS], stg[u * TPS]);
+                fence_async_smem();
+                mbar_arrive(full + slot);
+                request(q + 2 * NPROD, k & 1u);
+            }
+            if (!alive && wtid == 0) atomicExch(a.status, DCTP_DEV_MMA_TIMEOUT);
+        }
+    } else {
+        if (first < a.num_tiles) prefetch(first);
+    }
 
     const uint32_t slot_col = tmem + 128 + SLOT_COLS * wg;         // this slot's TMEM columns
     const uint32_t d_col = slot_col, a2_hi_col = slot_col + N1MAX, a2_lo_col = slot_col + N1MAX + N1MAX / 2;
@@ -211,6 +279,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     const uint32_t lo_bx_hi = smem_u32(bx_hi) >> 4, lo_bx_lo = smem_u32(bx_lo) >> 4;
     const uint32_t lo_c_hi = smem_u32(c_hi) >> 4, lo_c_lo = smem_u32(c_lo) >> 4;
 
+    uint32_t fill = 0;                                             // (NPROD) how many tiles this slot has consumed
     // MMA issue is straight-line code (step counts are template parameters): a runtime loop costs ~100 cycles of
     // dependent uniform-datapath work per MMA, three times the 32 cycles the tensor core needs for it.
     auto issue_stage1 = [&]() {                                    // D1 = A' * Bx^T : A'hi*Bxhi + A'hi*Bxlo + A'lo*Bxhi
@@ -223,6 +292,8 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
             default: detail::issue_ts3<8, KB16>(d_col, tmem, tmem, tmem + 64, b_hi_lo, b_lo_lo, b_hi_lo, desc_k, a.idesc); break;
         }
         mma_commit(bar);
+        if constexpr (NPROD > 0)                                   // the data operand may be overwritten once these have read it:
+            mma_commit(bxfree + wg * NPROD + ((fill + 1) * NSLOT + wg) % NPROD);   // tell the producer of the slot's next tile
     };
     auto issue_stage2 = [&]() {                                    // D2 = A2 * C^T : A2hi*Chi + A2lo*Chi + A2hi*Clo
         tc_fence_after_sync();
@@ -251,7 +322,6 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     const bool lane_in_map = my_g < (uint32_t)a.G && my_v < (uint32_t)a.N;
     const uint32_t bar_id = 1 + wg;
     uint32_t phase = 0;
-    bool alive = true;
 
     // final reduction roles, fixed for the whole kernel
     const uint32_t tpm = a.TPM;
@@ -265,7 +335,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
     auto stamp = [&](int k) {
         if (a.trace != nullptr && blockIdx.x == 0 && wtid == 0 && wg == 0 && trace_i < 32) a.trace[trace_i * 8 + k] = clock64();
     };
-    for (int tile = first; tile < a.num_tiles; tile += stride) {
+    for (int tile = (NPROD > 0 && wg >= (uint32_t)NSLOT) ? a.num_tiles : first; tile < a.num_tiles; tile += stride) {
         stamp(0);
         const int map0 = tile * a.MT;
         const int maps_here = min(a.MT, a.n_maps - map0);
@@ -276,7 +346,7 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
 #pragma unroll
             for (int u = 0; u < TSCORE_PF; ++u)
                 if (wtid + u * TPS < pf_full) detail::Scatter<VPE>::st(bx_hi, bx_lo, scat[wtid + u * TPS], stage[u * TPS]);
-        } else {
+        } else if constexpr (NPROD == 0) {
 #pragma unroll
             for (int u = 0; u < TSCORE_PF; ++u)
                 if (wtid + u * TPS < pf_full) detail::Scatter<VPE>::st(bx_hi, bx_lo, scat[wtid + u * TPS], pf[u]);
@@ -287,10 +357,18 @@ __global__ void __launch_bounds__(128 * NSLOT, 1) score_t_kernel(const TScoreArg
         named_bar_sync(bar_id, TPS);
         stamp(2);
         if (swarp == 0) {
-            if (elect_one()) issue_stage1();
+            if (elect_one()) {
+                if constexpr (NPROD > 0) {                         // a producer has written this tile's data operand
+                    if (alive && !mbar_wait(full + wg, fill & 1u)) alive = false;
+                }
+                issue_stage1();
+            }
             __syncwarp();
         }
-        if (tile + stride < a.num_tiles) prefetch(tile + stride);  // lands while the tensor core and the epilogues work
+        ++fill;
+        if constexpr (NPROD == 0) {
+            if (tile + stride < a.num_tiles) prefetch(tile + stride);  // lands while the tensor core and the epilogues work
+        }
         stamp(3);
         if (!mbar_wait(bar, phase)) { alive = false; break; }
         phase ^= 1;
