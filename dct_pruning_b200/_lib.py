@@ -8,8 +8,8 @@ import os
 
 from .build import LIB_PATH
 
-PATH_AUTO, PATH_UMMA, PATH_SIMT, PATH_TMEM, PATH_LARGE = 0, 1, 2, 3, 4
-PATHS = {'auto': PATH_AUTO, 'umma': PATH_UMMA, 'simt': PATH_SIMT, 'tmem': PATH_TMEM, 'large': PATH_LARGE}
+PATH_AUTO, PATH_UMMA, PATH_SIMT, PATH_TMEM, PATH_LARGE, PATH_STACK, PATH_KRON = 0, 1, 2, 3, 4, 5, 6
+PATHS = {'auto': PATH_AUTO, 'umma': PATH_UMMA, 'simt': PATH_SIMT, 'tmem': PATH_TMEM, 'large': PATH_LARGE, 'stack': PATH_STACK, 'kron': PATH_KRON}
 
 OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_DEVICE = 0, -1, -2, -3, -4
 

@@ -14,6 +14,8 @@
 #include "score_simt.cuh"
 #include "score_large.cuh"
 #include "score_tmem.cuh"
+#include "score_stack.cuh"
+#include "score_kron.cuh"
 #include "score_umma.cuh"
 #include "topk.cuh"
 #include "gather.cuh"
@@ -49,6 +51,14 @@ struct TBasis {                                                          // per 
     uint16_t* scatter = nullptr;                                         // [tile_vec][vpe]
     int tile_vec = 0, vpe = 1;
 };
+struct StackBasis {                                                      // per N: operands of the stacked-basis kernel
+    uint32_t* a_img = nullptr;                                           // [128][32] packed bf16 pairs, the TMEM image of the stacked basis
+    uint8_t *c2_hi = nullptr, *c2_lo = nullptr;                          // stage-2 basis operand images
+    uint16_t* table = nullptr;                                           // Bx offsets of a tile's float4 pieces
+    int kp = 0, vec = 0, tile_vec = 0;
+    uint32_t table_bytes = 0;
+};
+struct KronBasis { uint8_t *hi = nullptr, *lo = nullptr; };             // per N <= 8: C_N (x) C_N as a shared-memory operand image
 struct LargeBasis { uint16_t *hi = nullptr, *lo = nullptr; int NP = 0, NPR = 0; };   // operand image of C_N: [NP/64][NPR][64], see get_large_basis
 struct SimtBasis { float* t = nullptr; };                               // [N x N], t[n*N + k] = C_N[k][n]
 
@@ -62,6 +72,12 @@ struct State {
     std::map<int, SimtBasis> simt;                     // N
     std::map<int, TBasis> tmem;                        // N
     std::map<int, LargeBasis> large;                   // N
+    std::map<int, StackBasis> stack;                   // N
+    std::map<int, KronBasis> kron;                     // N
+    bool kron_on = true;                               // AUTO routes dense sides <= 8 to the Kronecker kernel (DCTP_KRON=0: round-1 kernels)
+    bool stack_on = true;                              // AUTO routes dense even sides to the stacked-basis kernel (DCTP_STACK=0: round-1 kernels)
+    long long stack_min_bytes = 0;                     // ... for launches of at least this many bytes (DCTP_STACK_MIN_MB)
+    void* encode_tiled = nullptr;                      // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link dependency)
     int t_slots = 3;                                   // tile slots per CTA of the TMEM-operand kernel (DCTP_T_SLOTS=0 disables it)
     bool t_all = false;
     bool t_prod = true;                                // 3-slot TMEM-operand kernel with two producer warpgroups where the tile fits
@@ -183,6 +199,212 @@ int get_t_basis(int N, TBasis& out) {
     return DCTP_OK;
 }
 
+// ------------------------------------------------------------------ stacked-basis kernel (score_stack.cuh)
+inline int stack_kp(int N) { return (N + 15) / 16 * 16; }
+inline int stack_sets(int kp) { return kp <= 32 ? 64 / kp : 1; }
+inline int stack_g(int kp) { return kp == 16 ? 8 : kp == 32 ? 4 : 2; }
+// dense square maps, even side 10..64; above 32 a tile is two maps, and 2*N*N must be a whole number of 128-byte rows
+bool stack_shape_supported(int N) { return N >= 10 && N <= 64 && (N % 2) == 0 && (N <= 32 || (N % 4) == 0); }
+
+int get_stack_basis(int N, StackBasis& out) {
+    auto it = g.stack.find(N);
+    if (it != g.stack.end()) { out = it->second; return DCTP_OK; }
+    using S = StackSmem;
+    const int KP = stack_kp(N), J = stack_sets(KP), G = stack_g(KP), NN = N * N, Np = (N + 7) / 8 * 8, MT = G * J;
+    std::vector<uint32_t> img(128 * 32, 0);
+    for (int lane = 0; lane < 128; ++lane) {
+        const int q = lane >> 5, part = (lane >> 4) & 1, r = lane & 15;
+        const int set = J == 4 ? q : J == 2 ? q >> 1 : 0;
+        const int v = J == 4 ? r : J == 2 ? 16 * (q & 1) + r : 16 * q + r;
+        if (v >= N) continue;
+        for (int w = 0; w < N; ++w) {
+            uint16_t h, l;
+            split_bf16(dct_coef(v, w, N), h, l);
+            const int k = set * KP + w;
+            img[lane * 32 + k / 2] |= static_cast<uint32_t>(part ? l : h) << (16 * (k & 1));
+        }
+    }
+    std::vector<uint8_t> chi(S::C2_HALF, 0), clo(S::C2_HALF, 0);
+    for (int u = 0; u < N; ++u)
+        for (int h = 0; h < N; ++h) {
+            uint16_t hh, ll;
+            split_bf16(dct_coef(u, h, N), hh, ll);
+            const size_t off = static_cast<size_t>(h / 8) * S::LBO2 + u * 16 + (h % 8) * 2;
+            std::memcpy(&chi[off], &hh, 2);
+            std::memcpy(&clo[off], &ll, 2);
+        }
+    StackBasis b;
+    b.kp = KP;
+    b.vec = (N % 4) == 0 ? 4 : 2;
+    b.tile_vec = MT * NN / 4;
+    const int pieces = b.vec == 4 ? 1 : 2;
+    std::vector<uint16_t> tab(static_cast<size_t>(b.tile_vec) * pieces + 8, 0);
+    for (int f = 0; f < b.tile_vec; ++f)
+        for (int pc = 0; pc < pieces; ++pc) {
+            const int e = 4 * f + 2 * pc, m = e / NN, rem = e % NN, h = rem / N, w = rem % N, gI = m / J, set = m % J;
+            const int n = gI * Np + h, k = set * KP + w;
+            tab[static_cast<size_t>(f) * pieces + pc] = static_cast<uint16_t>((k / 8) * S::LBO1 + n * 16 + (k % 8) * 2);
+        }
+    b.table_bytes = static_cast<uint32_t>((static_cast<size_t>(b.tile_vec) * pieces * 2 + 15) / 16 * 16);
+    if (b.table_bytes > S::TABLE_MAX) return fail(DCTP_E_UNSUPPORTED, "stacked-basis kernel: offset table of side %d does not fit", N);
+    CUDA_TRY(cudaMalloc(&b.a_img, img.size() * 4));
+    CUDA_TRY(cudaMalloc(&b.c2_hi, chi.size()));
+    CUDA_TRY(cudaMalloc(&b.c2_lo, clo.size()));
+    CUDA_TRY(cudaMalloc(&b.table, tab.size() * 2));
+    CUDA_TRY(cudaMemcpy(b.a_img, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.c2_hi, chi.data(), chi.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.c2_lo, clo.data(), clo.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.table, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice));
+    g.stack[N] = b;
+    out = b;
+    return DCTP_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <typename Args>
+cudaError_t launch_score_tma(void (*kern)(const CUtensorMap, const Args), int grid, int block, size_t smem, cudaStream_t stream,
+                             const CUtensorMap& map, const Args& args);
+
+int launch_stack(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
+    StackBasis basis;
+    int rc = get_stack_basis(N, basis);
+    if (rc) return rc;
+    StackArgs a;
+    std::memset(&a, 0, sizeof a);
+    const int KP = basis.kp, J = stack_sets(KP);
+    a.x_dense = first; a.n_maps = B * c_count; a.c_count = c_count;
+    a.N = N; a.NN = N * N; a.Np = (N + 7) / 8 * 8; a.G = stack_g(KP); a.MT = a.G * J;
+    a.total_elems = static_cast<long long>(a.n_maps) * a.NN;
+    a.ncols = a.G * a.Np;
+    a.tile_elems = a.MT * a.NN; a.tile_rows = a.tile_elems / 32; a.tile_vec = basis.tile_vec;
+    a.num_tiles = (a.n_maps + a.MT - 1) / a.MT;
+    a.tail_tile = (a.total_elems % 32) != 0 ? a.num_tiles - 1 : -1;
+    a.idesc1 = umma::make_idesc_bf16(128, a.ncols, false, false);
+    a.idesc2 = umma::make_idesc_bf16(128, KP, false, false);
+    a.a_img = basis.a_img; a.c2_hi = basis.c2_hi; a.c2_lo = basis.c2_lo; a.table = basis.table; a.table_bytes = basis.table_bytes;
+    a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
+    CUtensorMap map;
+    std::memset(&map, 0, sizeof map);
+    const long long rows = a.total_elems / 32;
+    if (rows > 0) {
+        cuuint64_t gdim[2] = {32, static_cast<cuuint64_t>(rows)};
+        cuuint64_t gstr[1] = {128};
+        cuuint32_t box[2] = {32, static_cast<cuuint32_t>(a.tile_rows)}, estr[2] = {1, 1};
+        const CUresult r = reinterpret_cast<EncodeTiledFn>(g.encode_tiled)(
+            &map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(first), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(DCTP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %lld rows, box %d", (int)r, rows, a.tile_rows);
+    }
+    int grid = g.sm_count < a.num_tiles ? g.sm_count : a.num_tiles;
+    const size_t smem = StackSmem::TOTAL;
+    const bool v4 = basis.vec == 4;
+    switch (KP) {
+        case 16: CUDA_TRY(v4 ? launch_score_tma(score_stack_kernel<16, 4>, grid, STACK_NT, smem, stream, map, a)
+                             : launch_score_tma(score_stack_kernel<16, 2>, grid, STACK_NT, smem, stream, map, a)); break;
+        case 32: CUDA_TRY(v4 ? launch_score_tma(score_stack_kernel<32, 4>, grid, STACK_NT, smem, stream, map, a)
+                             : launch_score_tma(score_stack_kernel<32, 2>, grid, STACK_NT, smem, stream, map, a)); break;
+        case 48: CUDA_TRY(launch_score_tma(score_stack_kernel<48, 4>, grid, STACK_NT, smem, stream, map, a)); break;
+        default: CUDA_TRY(launch_score_tma(score_stack_kernel<64, 4>, grid, STACK_NT, smem, stream, map, a)); break;
+    }
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    return DCTP_OK;
+}
+
+// ------------------------------------------------------------------ Kronecker kernel (score_kron.cuh), sides 1..8
+int get_kron_basis(int N, KronBasis& out) {
+    auto it = g.kron.find(N);
+    if (it != g.kron.end()) { out = it->second; return DCTP_OK; }
+    using S = StackSmem;
+    std::vector<uint8_t> hi(S::C2_HALF, 0), lo(S::C2_HALF, 0);
+    for (int u = 0; u < N; ++u)
+        for (int v = 0; v < N; ++v)
+            for (int h = 0; h < N; ++h)
+                for (int w = 0; w < N; ++w) {
+                    uint16_t hh, ll;
+                    split_bf16(dct_coef(u, h, N) * dct_coef(v, w, N), hh, ll);
+                    const int n = u * N + v, k = h * N + w;
+                    const size_t off = static_cast<size_t>(k / 8) * S::LBO2 + n * 16 + (k % 8) * 2;
+                    std::memcpy(&hi[off], &hh, 2);
+                    std::memcpy(&lo[off], &ll, 2);
+                }
+    KronBasis b;
+    CUDA_TRY(cudaMalloc(&b.hi, hi.size()));
+    CUDA_TRY(cudaMalloc(&b.lo, lo.size()));
+    CUDA_TRY(cudaMemcpy(b.hi, hi.data(), hi.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.lo, lo.data(), lo.size(), cudaMemcpyHostToDevice));
+    g.kron[N] = b;
+    out = b;
+    return DCTP_OK;
+}
+
+int launch_kron(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
+    KronBasis basis;
+    int rc = get_kron_basis(N, basis);
+    if (rc) return rc;
+    KronArgs a;
+    std::memset(&a, 0, sizeof a);
+    const int NN = N * N, K2 = (NN + 15) / 16 * 16;
+    const bool even = (N % 2) == 0;
+    a.x_dense = first; a.n_maps = B * c_count; a.c_count = c_count; a.N = N; a.NN = NN;
+    a.total_elems = static_cast<long long>(a.n_maps) * NN;
+    a.idesc = umma::make_idesc_bf16(128, K2, false, false);
+    a.k_hi = basis.hi; a.k_lo = basis.lo;
+    a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
+    a.tail_tile = -1;
+    CUtensorMap map;
+    std::memset(&map, 0, sizeof map);
+    CUresult r = CUDA_SUCCESS;
+    if (even) {
+        a.sub_tiles = N == 8 ? 1 : 2;
+        a.row_floats = NN + (((NN / 4) % 2) == 0 ? 4 : 0);            // an odd number of 16-byte units per row: conflict-free 128-bit reads
+        a.tile_maps = 128 * a.sub_tiles;
+        a.box_rows = a.tile_maps;
+        a.tile_bytes = static_cast<uint32_t>(a.tile_maps) * a.row_floats * 4u;
+        cuuint64_t gdim[2] = {static_cast<cuuint64_t>(NN), static_cast<cuuint64_t>(a.n_maps)};
+        cuuint64_t gstr[1] = {static_cast<cuuint64_t>(NN) * 4};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(a.row_floats), static_cast<cuuint32_t>(a.tile_maps)}, estr[2] = {1, 1};
+        r = reinterpret_cast<EncodeTiledFn>(g.encode_tiled)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(first), gdim, gstr, box, estr,
+                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        a.sub_tiles = N == 7 ? 1 : N == 5 ? 2 : 4;
+        a.row_floats = NN;
+        a.tile_maps = 128 * a.sub_tiles;
+        a.box_rows = a.tile_maps * NN / 32;
+        a.tile_bytes = static_cast<uint32_t>(a.box_rows) * 128u;
+        const long long rows = a.total_elems / 32;
+        if (rows > 0) {
+            cuuint64_t gdim[2] = {32, static_cast<cuuint64_t>(rows)};
+            cuuint64_t gstr[1] = {128};
+            cuuint32_t box[2] = {32, static_cast<cuuint32_t>(a.box_rows)}, estr[2] = {1, 1};
+            r = reinterpret_cast<EncodeTiledFn>(g.encode_tiled)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(first), gdim, gstr, box,
+                                                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+    }
+    if (r != CUDA_SUCCESS) return fail(DCTP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d maps of side %d", (int)r, a.n_maps, N);
+    a.num_tiles = (a.n_maps + a.tile_maps - 1) / a.tile_maps;
+    if (!even && (a.total_elems % 32) != 0) a.tail_tile = a.num_tiles - 1;
+    const int grid = g.sm_count < a.num_tiles ? g.sm_count : a.num_tiles;
+    const size_t smem = KronSmem::TOTAL;
+#define KRON_LAUNCH(K2V)                                                                                                         \
+    CUDA_TRY(even ? launch_score_tma(score_kron_kernel<K2V, true>, grid, KRON_NT, smem, stream, map, a)                         \
+                  : launch_score_tma(score_kron_kernel<K2V, false>, grid, KRON_NT, smem, stream, map, a))
+    switch (K2) {
+        case 16: KRON_LAUNCH(16); break;
+        case 32: KRON_LAUNCH(32); break;
+        case 48: KRON_LAUNCH(48); break;
+        default: KRON_LAUNCH(64); break;
+    }
+#undef KRON_LAUNCH
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    return DCTP_OK;
+}
+
 // stage-2 output chunks of the large-map kernel: NUC chunks of NU columns (multiple of 16, at most 128: one basis slab)
 void large_u_chunks(int N, int& nu, int& nuc) {
     nuc = (N + 127) / 128;
@@ -244,6 +466,22 @@ cudaError_t launch_score(void (*kern)(const Args), int grid, int block, size_t s
     cfg.attrs = attr;
     cfg.numAttrs = g.pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
+template <typename Args>
+cudaError_t launch_score_tma(void (*kern)(const CUtensorMap, const Args), int grid, int block, size_t smem, cudaStream_t stream,
+                             const CUtensorMap& map, const Args& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(block));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, map, args);
 }
 
 // ------------------------------------------------------------------ init
@@ -311,6 +549,29 @@ int ensure_init() {
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
     }
+    {
+        const void* fns[] = {reinterpret_cast<const void*>(score_stack_kernel<16, 4>), reinterpret_cast<const void*>(score_stack_kernel<16, 2>),
+                             reinterpret_cast<const void*>(score_stack_kernel<32, 4>), reinterpret_cast<const void*>(score_stack_kernel<32, 2>),
+                             reinterpret_cast<const void*>(score_stack_kernel<48, 4>), reinterpret_cast<const void*>(score_stack_kernel<64, 4>)};
+        for (const void* fn : fns) {
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(StackSmem::TOTAL)));
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+        const void* kfns[] = {reinterpret_cast<const void*>(score_kron_kernel<16, true>), reinterpret_cast<const void*>(score_kron_kernel<16, false>),
+                              reinterpret_cast<const void*>(score_kron_kernel<32, true>), reinterpret_cast<const void*>(score_kron_kernel<32, false>),
+                              reinterpret_cast<const void*>(score_kron_kernel<48, true>), reinterpret_cast<const void*>(score_kron_kernel<48, false>),
+                              reinterpret_cast<const void*>(score_kron_kernel<64, true>), reinterpret_cast<const void*>(score_kron_kernel<64, false>)};
+        for (const void* fn : kfns) {
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(KronSmem::TOTAL)));
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &g.encode_tiled, cudaEnableDefault, &qres));
+        if (!g.encode_tiled) return fail(DCTP_E_CUDA, "the driver does not export cuTensorMapEncodeTiled");
+    }
+    if (const char* e = std::getenv("DCTP_KRON")) g.kron_on = std::atoi(e) != 0;
+    if (const char* e = std::getenv("DCTP_STACK")) g.stack_on = std::atoi(e) != 0;
+    if (const char* e = std::getenv("DCTP_STACK_MIN_MB")) g.stack_min_bytes = static_cast<long long>(std::atoi(e)) << 20;
     if (const char* e = std::getenv("DCTP_TP")) g.t_prod = std::atoi(e) != 0;
     if (const char* e = std::getenv("DCTP_PDL")) g.pdl = std::atoi(e) != 0;
     if (const char* e = std::getenv("DCTP_LARGE_LO")) g.large_lo = std::atoi(e);
@@ -511,6 +772,10 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
     const float* first = x + static_cast<long long>(c_begin) * stride_c;
     const bool dense = basis.scatter != nullptr && stride_c == a.NN && (B == 1 || stride_b == static_cast<long long>(c_count) * a.NN) &&
                        (reinterpret_cast<uintptr_t>(first) % 16) == 0;
+    if (KP == 64 && allow_t && dense && g.kron_on && N <= 8) return launch_kron(first, B, N, c_count, accum, energy_out, coeff_out, stream);
+    if (KP == 64 && allow_t && dense && g.stack_on && stack_shape_supported(N) &&
+        static_cast<long long>(a.n_maps) * a.NN * 4 >= g.stack_min_bytes)
+        return launch_stack(first, B, N, c_count, accum, energy_out, coeff_out, stream);
     if (KP == 64 && allow_t && dense && t_stream_ok(N, a.n_maps) && t_launch_ok(N, static_cast<long long>(a.n_maps) * a.NN * 4))
         return launch_t(first, B, N, c_count, accum, energy_out, coeff_out, stream);
     int mode;
@@ -614,7 +879,9 @@ int dctp_shutdown(void) {
     for (auto& kv : g.tmem) {
         cudaFree(kv.second.a_hi); cudaFree(kv.second.a_lo); cudaFree(kv.second.c_hi); cudaFree(kv.second.c_lo); cudaFree(kv.second.scatter);
     }
-    g.umma.clear(); g.simt.clear(); g.tmem.clear(); g.large.clear();
+    for (auto& kv : g.stack) { cudaFree(kv.second.a_img); cudaFree(kv.second.c2_hi); cudaFree(kv.second.c2_lo); cudaFree(kv.second.table); }
+    for (auto& kv : g.kron) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
+    g.umma.clear(); g.simt.clear(); g.tmem.clear(); g.large.clear(); g.stack.clear(); g.kron.clear();
     cudaFree(g.status); cudaFree(g.hx); cudaFree(g.hacc); cudaFree(g.hout);
     g = State();
     return DCTP_OK;
@@ -644,6 +911,16 @@ int dctp_prepare(int H, int W) {
     if (rc) return rc;
     if (H < 1 || W < 1) return fail(DCTP_E_INVALID, "dctp_prepare: H=%d W=%d", H, W);
     if (umma_shape_ok(H, W, W)) {
+        if (H <= 8) {
+            KronBasis kb;
+            int rc2 = get_kron_basis(H, kb);
+            if (rc2) return rc2;
+        }
+        if (stack_shape_supported(H)) {
+            StackBasis sb;
+            int rc2 = get_stack_basis(H, sb);
+            if (rc2) return rc2;
+        }
         if (t_shape_ok(H)) {
             TBasis tb;
             int rc2 = get_t_basis(H, tb);
@@ -674,7 +951,7 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
     if (B < 0 || H < 1 || W < 1 || c_begin < 0 || c_count < 0 || stride_h < W)
         return fail(DCTP_E_INVALID, "dctp_score_accum: B=%d H=%d W=%d c_begin=%d c_count=%d stride_h=%lld", B, H, W, c_begin,
                     c_count, stride_h);
-    if (path < DCTP_PATH_AUTO || path > DCTP_PATH_LARGE) return fail(DCTP_E_INVALID, "unknown path %d", path);
+    if (path < DCTP_PATH_AUTO || path > DCTP_PATH_KRON) return fail(DCTP_E_INVALID, "unknown path %d", path);
     if (B == 0 || c_count == 0) return DCTP_OK;                     // empty batch / empty window: nothing to add
     if (!x || !accum) return fail(DCTP_E_INVALID, "dctp_score_accum: null pointer");
     if (static_cast<long long>(B) * c_count > (1ll << 30)) return fail(DCTP_E_INVALID, "too many maps in one call");
@@ -695,6 +972,22 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
                 return fail(DCTP_E_UNSUPPORTED, "TMEM-operand path takes dense 16-B aligned square maps of side 5..64 (odd sides: up to 13, and a whole "
                                                 "number of float4 in the call) (got %dx%d)", H, W);
             return launch_t(first, B, H, c_count, accum, energy_out, coeff_out, s);
+        }
+        case DCTP_PATH_KRON: {
+            const float* first = x + static_cast<long long>(c_begin) * stride_c;
+            const bool dense = stride_h == W && stride_c == static_cast<long long>(H) * W &&
+                               (B == 1 || stride_b == static_cast<long long>(c_count) * H * W) && (reinterpret_cast<uintptr_t>(first) % 16) == 0;
+            if (H != W || H > 8 || !dense)
+                return fail(DCTP_E_UNSUPPORTED, "Kronecker path takes dense 16-B aligned square maps of side <= 8 (got %dx%d)", H, W);
+            return launch_kron(first, B, H, c_count, accum, energy_out, coeff_out, s);
+        }
+        case DCTP_PATH_STACK: {
+            const float* first = x + static_cast<long long>(c_begin) * stride_c;
+            const bool dense = stride_h == W && stride_c == static_cast<long long>(H) * W &&
+                               (B == 1 || stride_b == static_cast<long long>(c_count) * H * W) && (reinterpret_cast<uintptr_t>(first) % 16) == 0;
+            if (H != W || !stack_shape_supported(H) || !dense)
+                return fail(DCTP_E_UNSUPPORTED, "stacked-basis path takes dense 16-B aligned square maps of even side 10..64 (above 32: multiples of 4) (got %dx%d)", H, W);
+            return launch_stack(first, B, H, c_count, accum, energy_out, coeff_out, s);
         }
         case DCTP_PATH_LARGE: {
             const float* first = x + static_cast<long long>(c_begin) * stride_c;

@@ -165,6 +165,41 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[16]
 __device__ __forceinline__ void tmem_st_wait() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// 16 lanes x 16 consecutive fp32 columns in the mma-fragment arrangement (probe P1, tools/probe_r2.cu): with t the thread
+// index in the warp, v[4g + 0,1] = (lane base + t/4,     column 8g + 2(t%4) + 0,1)
+//                    v[4g + 2,3] = (lane base + t/4 + 8, column 8g + 2(t%4) + 0,1)      (lane base: a multiple of 16)
+__device__ __forceinline__ void tmem_ld_frag16(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_frag8(uint32_t taddr, uint32_t (&v)[4]) {      // 16 lanes x 8 columns
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+// registers -> 16 lanes x 8 (x2) / 4 (x1) consecutive 32-bit columns: v[2g + 0] = (lane base + t/4, column 4g + t%4),
+// v[2g + 1] = (lane base + t/4 + 8, same column)   (probe P7)
+__device__ __forceinline__ void tmem_st_frag8(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_frag4(uint32_t taddr, uint32_t v0, uint32_t v1) {
+    asm volatile("tcgen05.st.sync.aligned.16x128b.x1.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(v0), "r"(v1) : "memory");
+}
+// 2-D tiled TMA load (tensor map in kernel parameter space / __grid_constant__): box -> dense rows in shared memory,
+// out-of-bounds rows arrive as zeros and still count towards the transaction bytes (probe P6)
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 // named barrier over `threads` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -242,6 +277,25 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     float ra = a - __uint_as_float(hi << 16);
     float rb = b - __uint_as_float(hi & 0xFFFF0000u);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
+// the same split for an fp32 pair held in a 64-bit register pair (a in the low word): the residual comes from one packed
+// subtraction (FADD2 on sm_100)
+__device__ __forceinline__ void split2_packed(uint64_t ab, uint32_t& hi, uint32_t& lo) {
+    const float a = __uint_as_float(static_cast<uint32_t>(ab)), b = __uint_as_float(static_cast<uint32_t>(ab >> 32));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const uint64_t h2 = (static_cast<uint64_t>(hi & 0xFFFF0000u) << 32) | static_cast<uint64_t>(hi << 16);
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ab), "l"(h2));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(__uint_as_float(static_cast<uint32_t>(r >> 32))), "f"(__uint_as_float(static_cast<uint32_t>(r))));
+}
+__device__ __forceinline__ uint64_t add2_packed(uint64_t x, uint64_t y) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack2(uint32_t lo_word, uint32_t hi_word) {
+    return (static_cast<uint64_t>(hi_word) << 32) | lo_word;
 }
 
 }  // namespace umma

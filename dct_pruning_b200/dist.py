@@ -33,6 +33,10 @@ def shutdown():
         dist.destroy_process_group()
 
 
+def world_size(group=None):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
 def allreduce_sums(flat, group=None):
     """Sum the flat per-layer score buffer (last entry = image count) over all ranks, in place.
     The only collective of the scoring path; a no-op in a single process."""

@@ -61,6 +61,9 @@ def device_batches(host_batches, device):
         if bufs[slot] is None or bufs[slot].shape != x.shape or bufs[slot].dtype != x.dtype:
             bufs[slot] = torch.empty(x.shape, dtype=x.dtype, device=device)
             consumed[slot] = None
+            # a fresh block may be one the caching allocator just took back from activations of a forward pass that is still
+            # running on the main stream (ragged last batch): order the first copy into it behind that work
+            copy_stream.wait_stream(main)
         with torch.cuda.stream(copy_stream):
             if consumed[slot] is not None:
                 copy_stream.wait_event(consumed[slot])      # the forward pass that read this buffer has finished
@@ -135,6 +138,10 @@ def imp_score(net, args, loader=None, out_root='importance_score', write=True, p
         loader = synthetic_batches(args.batch_size, side, args.limit,
                                    seed_base=getattr(args, 'seed_base', 1000), as_dict=(args.net == 'u2netp'))
     session = ScoreSession(net, args.net, path=path)
+    if world > 1:                                       # same flat layout on every rank, also on one whose shards are all empty
+        _, side0 = NET_INPUT[args.net]
+        side0 = getattr(args, 'input_side', None) or side0
+        session.plan_layout(torch.zeros(1, 3, side0, side0, device=device))
     with session:
         inference(net, loader, args.limit, device, rank=rank, world=world)
     files = session.finalize()

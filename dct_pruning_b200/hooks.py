@@ -92,8 +92,15 @@ class ScoreSession:
                 c_begin, c_count = 0, C
             off = self._slot(idx, c_count, t.device)
             plan = self._plans[idx] = (C, c_begin, c_count, self.flat.data_ptr() + 8 * off)
-        code = self._score_accum(t.data_ptr(), B, H, W, sb, sc, sh, plan[1], plan[2], plan[3], None, None, self.path,
-                                 torch.cuda.current_stream().cuda_stream)
+        # launch on the activation's own device and on that device's current stream (the hook may fire while another
+        # device is current); the library refuses a device other than the one it was initialised on
+        if t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                code = self._score_accum(t.data_ptr(), B, H, W, sb, sc, sh, plan[1], plan[2], plan[3], None, None, self.path,
+                                         torch.cuda.current_stream(t.device).cuda_stream)
+        else:
+            code = self._score_accum(t.data_ptr(), B, H, W, sb, sc, sh, plan[1], plan[2], plan[3], None, None, self.path,
+                                     torch.cuda.current_stream(t.device).cuda_stream)
         if code:
             _lib.check(code)
         self.images[idx] += B
@@ -101,8 +108,9 @@ class ScoreSession:
 
     def _slot(self, idx, c_count, device):
         if self.flat is None:
-            with torch.cuda.device(device):
-                _lib.check(self.lib.dctp_init())
+            if torch.device(device).type == 'cuda':
+                with torch.cuda.device(device):
+                    _lib.check(self.lib.dctp_init())
             self.flat = torch.zeros(self.capacity + 1, dtype=torch.float64, device=device)
         slot = self.slots[idx]
         if slot is None:
@@ -114,6 +122,36 @@ class ScoreSession:
             raise ValueError('site %r changed width: %d -> %d channels' % (self.sites[idx].module, slot[1], c_count))
         return slot[0]
 
+    def plan_layout(self, example):
+        """Allocate every site's accumulator slot ahead of the run, in site order, from one shape-only forward pass of
+        `example` (a [1,3,S,S] tensor on the net's device; nothing is scored).  Under torchrun every rank calls this, so all
+        ranks hold the same flat layout and enter the run's single all-reduce even when a rank's shard of the batches is
+        empty (batch size smaller than the world size)."""
+        shapes = [None] * len(self.sites)
+        taps = []
+        for idx, site in enumerate(self.sites):
+            def tap(module, inputs, output, idx=idx, take_input=(site.variant == VARIANT_INPUT)):
+                shapes[idx] = tuple((inputs[0] if take_input else output).shape)
+            taps.append(resolve_module(self.net, site.module).register_forward_hook(tap))
+        live, self.handles = self.handles, []
+        for h in live:
+            h.remove()
+        try:
+            with torch.no_grad():
+                self.net(example)
+        finally:
+            for h in taps:
+                h.remove()
+            if live:
+                self.register()
+        for idx, (site, shape) in enumerate(zip(self.sites, shapes)):
+            if shape is None:
+                continue
+            C = shape[1]
+            c_count = DENSENET_WINDOW if site.variant == VARIANT_LAST12 else C
+            self._slot(idx, c_count, example.device)
+        return self
+
     # ------------------------------------------------------------------ CUDA-graph replay (launch-bound nets)
     def capture(self, example, warmup=2):
         """Capture one forward pass with every hook launch in a CUDA graph and return `replay(x)`.
@@ -124,6 +162,9 @@ class ScoreSession:
         scores one more batch, exactly like calling `net(x)` with the hooks live."""
         if not self.handles:
             raise RuntimeError('register the hooks before capturing (with session: ...)')
+        if any(self.images):
+            raise RuntimeError('capture() restarts the run (its warm-up passes are discarded with reset()); call it before the '
+                               'first batch is scored, not after %d images' % max(self.images))
         static_in = example.detach().clone()
         side = torch.cuda.Stream(device=static_in.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -168,22 +209,42 @@ class ScoreSession:
         host = device_scores.cpu().numpy()
         return self.split_files(host)
 
-    def finalize_device(self, group=None, check=True):
-        fired = [n for n, s in zip(self.images, self.slots) if s is not None]
-        if self.flat is None or not fired:
-            raise RuntimeError('no hook fired: nothing to finalize')
-        if len(set(fired)) != 1:
-            raise RuntimeError('hook sites saw different image counts: %s' % sorted(set(fired)))
+    def reduce_sums(self, group=None):
+        """The run's one collective: the flat fp64 sums, with the image count in the slot after the last score, summed over
+        the ranks (a no-op in a single process).  Every rank enters it - also one whose shard was empty (its hooks never
+        fired: zeros, count 0; `plan_layout` gave it the layout) - and the consistency checks run AFTER it, so that a bad
+        rank cannot leave the others waiting in NCCL.  Returns the global image count."""
+        from .dist import allreduce_sums, world_size
+        fired = sorted(set(n for n, s in zip(self.images, self.slots) if s is not None))
         n = self.used
-        self.flat[n] = float(fired[0])
-        from .dist import allreduce_sums
-        allreduce_sums(self.flat[:n + 1], group=group)        # one collective per run; no-op single process
+        problem = None
+        if self.flat is None:
+            if world_size(group) > 1:
+                problem = 'this rank holds no accumulator layout (call plan_layout() before a multi-rank run)'
+            else:
+                raise RuntimeError('no hook fired: nothing to finalize')
+        elif len(fired) > 1:
+            problem = 'hook sites saw different image counts: %s' % fired
+        if self.flat is not None:
+            self.flat[n] = float(fired[0]) if len(fired) == 1 else float('nan')
+            allreduce_sums(self.flat[:n + 1], group=group)
+        if problem is not None:
+            raise RuntimeError(problem)
         n_images = float(self.flat[n].item())
+        if not n_images > 0:                                   # nan (a rank reported a problem) or nothing scored anywhere
+            raise RuntimeError('no hook fired on any rank (or a rank reported inconsistent image counts): nothing to finalize')
         self.n_images = n_images
+        return n_images
+
+    def finalize_device(self, group=None, check=True):
+        n_images = self.reduce_sums(group=group)
+        n = self.used
         out = torch.empty(n, dtype=torch.float32, device=self.flat.device)
-        _lib.check(self.lib.dctp_finalize(_lib.ptr(self.flat), n_images, _lib.ptr(out), n, _lib.current_stream()))
-        if check:
-            _lib.check(self.lib.dctp_check(_lib.current_stream()))
+        with torch.cuda.device(self.flat.device):
+            _lib.check(self.lib.dctp_finalize(_lib.ptr(self.flat), n_images, _lib.ptr(out), n,
+                                              torch.cuda.current_stream(self.flat.device).cuda_stream))
+            if check:
+                _lib.check(self.lib.dctp_check(torch.cuda.current_stream(self.flat.device).cuda_stream))
         return out
 
     def split_files(self, host_scores):

@@ -42,6 +42,10 @@ extern "C" {
 #define DCTP_PATH_SIMT   2        /* fp32 CUDA-core kernels; any H x W, strided rows */
 #define DCTP_PATH_TMEM   3        /* tcgen05 kernel with TMEM-resident operands; dense square maps, side 5..64 (odd sides up to 13) */
 #define DCTP_PATH_LARGE  4        /* tiled tcgen05 kernel; dense square maps, side 80..320, side % 16 == 0 (AUTO: from 96) */
+#define DCTP_PATH_STACK  5        /* warp-specialised tcgen05 kernel, TMA-staged tiles, stacked hi/lo basis in TMEM; dense square maps,
+                                     even side 10..64 (above 32: multiples of 4).  AUTO's choice for these shapes */
+#define DCTP_PATH_KRON   6        /* single-stage Kronecker tcgen05 kernel (C_N (x) C_N resident in shared memory, one map per TMEM
+                                     lane, TMA-staged tiles); dense square maps of side <= 8.  AUTO's choice for these shapes */
 
 int dctp_version(void);
 const char* dctp_last_error(void);

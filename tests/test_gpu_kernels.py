@@ -77,6 +77,52 @@ def test_tmem_operand_kernel(lib, cuda_device, n):
     assert np.abs(co.cpu().numpy() - z).max() / np.abs(z).max() < 2e-5
 
 
+@pytest.mark.parametrize('n', [1, 2, 3, 4, 5, 6, 7, 8])
+def test_kronecker_kernel(lib, cuda_device, n):
+    """Single-stage Kronecker kernel (sides <= 8): several tiles per CTA, ragged last tile, a stream that does not end on a
+    128-byte row (odd sides), the coefficient dump, exact zeros."""
+    from scipy.fft import dctn
+    from dct_pruning_b200.ops import dct_energy
+    for shape, seed in (((5, 131, n, n), 610 + n), ((1, 3, n, n), 710 + n), ((64, 2048, n, n), 810 + n)):
+        x = relu_maps(shape, seed=seed, dead_every=6)
+        acc, en, _ = dct_energy(x.to(cuda_device), path='kron', want_energy=True)
+        want = port.energy_parseval64(x.numpy()) if shape[0] == 64 else port.energy_scipy64(x.numpy())
+        en = en.cpu().numpy()
+        live = want > 0
+        assert (en[~live] == 0).all()
+        assert rel_err(en[live], want[live]).max() < ENERGY_TOL, shape
+        np.testing.assert_allclose(acc.cpu().numpy(), en.astype(np.float64).sum(0), rtol=1e-12)
+    small = relu_maps((2, 5, n, n), seed=910 + n)
+    _, _, co = dct_energy(small.to(cuda_device), path='kron', want_coeff=True)
+    z = dctn(small.numpy().astype(np.float64), type=2, norm='ortho', axes=(-2, -1))
+    assert np.abs(co.cpu().numpy() - z).max() / np.abs(z).max() < 2e-5
+
+
+STACK_SIDES = [10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 44, 48, 52, 56, 60, 64]
+
+
+@pytest.mark.parametrize('n', STACK_SIDES)
+def test_stacked_basis_kernel(lib, cuda_device, n):
+    """The warp-specialised stacked-basis kernel (TMA-staged tiles, hi/lo basis stacked along the TMEM lanes) on every
+    side it takes: many tiles per CTA, a ragged last tile, a stream that does not end on a 128-byte row (the tile that
+    is converted straight from global memory), the coefficient dump, exact zeros."""
+    from scipy.fft import dctn
+    from dct_pruning_b200.ops import dct_energy
+    for shape, seed in (((5, 131, n, n), 600 + n), ((1, 3, n, n), 700 + n), ((2, 700, n, n), 800 + n)):
+        x = relu_maps(shape, seed=seed, dead_every=6)
+        acc, en, _ = dct_energy(x.to(cuda_device), path='stack', want_energy=True)
+        want = port.energy_scipy64(x.numpy())
+        en = en.cpu().numpy()
+        live = want > 0
+        assert (en[~live] == 0).all()
+        assert rel_err(en[live], want[live]).max() < ENERGY_TOL, shape
+        np.testing.assert_allclose(acc.cpu().numpy(), en.astype(np.float64).sum(0), rtol=1e-12)
+    small = relu_maps((2, 5, n, n), seed=900 + n)
+    _, _, co = dct_energy(small.to(cuda_device), path='stack', want_coeff=True)
+    z = dctn(small.numpy().astype(np.float64), type=2, norm='ortho', axes=(-2, -1))
+    assert np.abs(co.cpu().numpy() - z).max() / np.abs(z).max() < 2e-5
+
+
 @pytest.mark.parametrize('n', [4, 7, 8, 10, 14, 20, 28, 40, 56, 64, 80, 128])
 @pytest.mark.parametrize('path', ['umma', 'simt'])
 def test_coefficients_match_scipy(lib, cuda_device, n, path):
