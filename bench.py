@@ -14,8 +14,11 @@ all-reduce, the finalise kernel and the segmented top-k, all inside the timed re
             feature maps of one batch, 9.2 GB per GPU: larger than L2, nothing to flush)
   e2e       images/s of complete importance generation through the public API: pinned host batch ->
             H2D -> cuDNN fp32 forward with all hooks live -> D2H of the running score sums, every step
-  roofline  dominant kernel (largest share of the step; the 56^2 layers' kernel on ResNet-50) timed with CUDA events
-            inside the timed region; algorithmic bytes = 4*H*W per scored map
+  roofline  dominant kernel (largest share of the step) timed with CUDA events; per launch the bound is the slower of
+            4*H*W bytes per scored map at the measured HBM peak and 3 x 2*H*W*(H+W) FLOPs at the measured bf16 peak (DESIGN.md);
+            kernel names come from the library (dctp_last_kernel), not from a copy of its dispatch
+  strong    the same run with ONE global batch of 256 split over the ranks (rank_slice, what the CLI does)
+  u2netp    BASELINE config 5: U^2-Netp at 320 and 288, batch 12 per GPU, in the same line
   cpu_baseline  the oracle port of the reference hooks on this box's host cores, bounded sample
 
 `--impl reference` times the reference's CPU implementation (oracle/reference_port.py: the
@@ -68,6 +71,8 @@ def parse():
                    help="kernel path of the hook launches (the whole net must fit a forced path, so 'tmem' / 'large' are left to 'auto')")
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-e2e', action='store_true')
+    p.add_argument('--no-strong', action='store_true', help='skip the strong-scaling leg (global batch split over the ranks)')
+    p.add_argument('--no-u2netp', action='store_true', help='skip the U^2-Netp 320/288 summary (BASELINE config 5)')
     p.add_argument('--graph', action='store_true', help='replay CUDA graphs (hook launches of a step; forward + hooks in the e2e leg): takes the host out of launch-bound nets')
     return p.parse_args()
 
@@ -156,55 +161,60 @@ def barrier(world):
 
 
 # ====================================================================== our arm
-def run_ours(args):
+PASSES = 3            # bf16 split-precision passes the binding roofline charges per contraction (hi*hi + lo*hi + hi*lo)
+
+
+def site_roofline(shape, scored_channels, hbm_gbs, tflops):
+    """Binding roofline of one hook launch: bytes = 4*H*W per scored map read once, FLOPs = 2*H*W*(H+W) per map
+    and pass.  Returns (algorithmic bytes, seconds the slower of the two limits allows, 'hbm' | 'tensor')."""
+    B, _, H, W = shape
+    maps = B * scored_channels
+    nbytes = 4 * maps * H * W
+    flops = PASSES * 2.0 * maps * H * W * (H + W)
+    t_mem, t_mma = nbytes / (hbm_gbs * 1e9), flops / (tflops * 1e12)
+    return nbytes, flops, max(t_mem, t_mma), ('hbm' if t_mem >= t_mma else 'tensor')
+
+
+def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, steps, with_e2e, npy_dir=None, clock_sampler=None):
+    """Kernel-only and end-to-end legs for one net at per-rank batch B.  Returns a dict (all times already max over ranks)."""
     from dct_pruning_b200 import _lib
     from dct_pruning_b200.compress import get_compress_rate, selection_plan
-    from dct_pruning_b200.generate import device_batches
+    from dct_pruning_b200.generate import device_batches, write_score_files
     from dct_pruning_b200.hooks import ScoreSession
     from dct_pruning_b200.sites import VARIANT_INPUT, resolve_module
     from dct_pruning_b200.topk import topk_segmented
     from dct_pruning_b200.zoo import get_network
 
-    rank, local_rank, world = dist_setup(args)
-    device = torch.device('cuda', local_rank)
-    torch.cuda.set_device(device)
-    wl = WORKLOADS[args.net]
-    B = args.batch or wl['batch']
-    side = wl['side']
-    torch.backends.cudnn.allow_tf32 = False            # activations fp32-exact, like the reference's
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.benchmark = True
-    lib = _lib.load()
-    _lib.check(lib.dctp_init())
-
+    wl = WORKLOADS[net_name]
     torch.manual_seed(0)
-    net = get_network(args.net).to(device).eval()
+    net = get_network(net_name).to(device).eval()
     g = torch.Generator().manual_seed(1000 + rank)
-    host_batch = torch.randn(B, 3, side, side, generator=g).pin_memory()
+    host_batch = torch.randn(max(B, 1), 3, side, side, generator=g)[:B].contiguous().pin_memory()
+    session = ScoreSession(net, net_name, path=args.path)
+    if world > 1:
+        session.plan_layout(torch.zeros(1, 3, side, side, device=device))
+    out = {'batch_per_gpu': B, 'input_side': side}
 
-    # ---- capture the hooked feature maps of one batch (resident in HBM for the kernel-only leg)
-    session = ScoreSession(net, args.net, path=args.path)
+    # ---- the hooked feature maps of one batch, resident in HBM for the kernel-only leg
     acts = [None] * len(session.sites)
-    handles = []
-    for idx, site in enumerate(session.sites):
-        def cap(module, inputs, output, idx=idx, take_input=(site.variant == VARIANT_INPUT)):
-            acts[idx] = (inputs[0] if take_input else output).detach().clone()
-        handles.append(resolve_module(net, site.module).register_forward_hook(cap))
-    with torch.no_grad():
-        net(host_batch.to(device))
-    for h in handles:
-        h.remove()
+    if B > 0:
+        handles = []
+        for idx, site in enumerate(session.sites):
+            def cap(module, inputs, output, idx=idx, take_input=(site.variant == VARIANT_INPUT)):
+                acts[idx] = (inputs[0] if take_input else output).detach().clone()
+            handles.append(resolve_module(net, site.module).register_forward_hook(cap))
+        with torch.no_grad():
+            net(host_batch.to(device))
+        for h in handles:
+            h.remove()
     torch.cuda.synchronize()
-    act_bytes = sum(a.numel() * 4 for a in acts)
-    # algorithmic bytes: only the scored channel window of each site is read
-    site_bytes = []
-    for a, site in zip(acts, session.sites):
-        c = 12 if site.variant == 'D' else a.shape[1]
-        site_bytes.append(4 * a.shape[0] * c * a.shape[2] * a.shape[3])
-    alg_bytes_step = sum(site_bytes)
-
-    # top-k plan on the flat score vector (segments = the files the reference's loader reads)
-    plan = selection_plan(args.net, get_compress_rate(wl['rate']))
+    live = [i for i, a in enumerate(acts) if a is not None]
+    scored = {i: (12 if session.sites[i].variant == 'D' else acts[i].shape[1]) for i in live}
+    hbm_peak, tflops, peak_kind = measured_peaks()
+    roof = {i: site_roofline(tuple(acts[i].shape), scored[i], hbm_peak, tflops) for i in live}
+    act_bytes = sum(acts[i].numel() * 4 for i in live)
+    alg_bytes_step = sum(roof[i][0] for i in live)
+    plan = selection_plan(net_name, get_compress_rate(wl['rate']))
 
     def finish_run():
         scores = session.finalize_device(check=False)
@@ -218,206 +228,314 @@ def run_ours(args):
         kept = topk_segmented(torch.cat(pieces), offsets, ks) if plan else []
         return scores, kept
 
-    # clocks are sampled from here to the end of the end-to-end leg: both timed regions lie inside the window
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    # ---- warm-up (bases uploaded, slots allocated, clocks up)
+    def one_step():
+        for i in live:
+            session.score(i, acts[i])
+
+    # ---- warm-up (bases uploaded, slots allocated, clocks up), then the kernel the library picked for every site
     for _ in range(max(args.warmup, 3)):
-        for idx, a in enumerate(acts):
-            session.score(idx, a)
+        one_step()
     finish_run()
     _lib.check(lib.dctp_check(None))
     session.reset()
-
-    # which kernel a site's launch runs (mirrors the dispatch in csrc/dctp.cu for dense activations)
-    def kernel_of(a):
-        n = a.shape[2]
-        if a.shape[2] == a.shape[3] and 96 <= n <= 320 and n % 16 == 0:
-            return 'score_large_kernel (tcgen05, tiled, 16 warps)'
-        if a.shape[2] != a.shape[3] or n > 128:
-            return 'score_simt_kernel (fp32 CUDA cores)'
-        if n > 64:
-            return 'score_umma_kernel<128> (tcgen05, smem operands)'
-        if n in (52, 56):
-            return 'score_t_kernel<64,3> (tcgen05, TMEM-resident operands, 2 producer warpgroups)'
-        if n % 2 == 0 and 52 <= n <= 64:
-            return 'score_t_kernel<64,3> (tcgen05, TMEM-resident operands, register prefetch)'
-        if n % 2 == 0 and 10 <= n <= 32 and a.numel() * 4 >= (32 << 20):
-            return 'score_t_kernel<32,6> (tcgen05, TMEM-resident operands, cp.async staging)'
-        mode = 0 if n % 4 == 0 else 1 if n % 2 == 0 else 2
-        return 'score_umma_kernel<64,%d,1> (tcgen05 bf16x3, smem operands, register prefetch)' % mode
-    site_kernel = [kernel_of(a) for a in acts]
-    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in acts]
-          for _ in range(args.steps)]
+    site_kernel = {}
+    for i in live:
+        session.score(i, acts[i])
+        site_kernel[i] = lib.dctp_last_kernel().decode()
+    torch.cuda.synchronize()
+    session.reset()
 
     # ---- the timed region: K steps of back-to-back hook launches + the end-of-run kernels, nothing else on the stream
-    barrier(world)
-    launches0 = lib.dctp_launch_count()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     step_graph = None
-    if args.graph:                                # launch-bound nets: one CUDA graph per step takes the host out of the loop
+    if args.graph and live:
         warm_stream = torch.cuda.Stream(device=device)
         warm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(warm_stream):
-            for idx, a in enumerate(acts):
-                session.score(idx, a)
+            one_step()
         torch.cuda.current_stream().wait_stream(warm_stream)
         torch.cuda.synchronize()
         step_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(step_graph):
-            for idx, a in enumerate(acts):
-                session.score(idx, a)
+            one_step()
         session.reset()
-        launches0 = lib.dctp_launch_count()
+    barrier(world)
+    launches0 = lib.dctp_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for step in range(args.steps):
+    for step in range(steps):
         if step_graph is not None:
             step_graph.replay()
-            for idx in range(len(acts)):
-                session.images[idx] += B
+            for i in live:
+                session.images[i] += B
         else:
-            for idx, a in enumerate(acts):
-                session.score(idx, a)
-    scores, kept = finish_run()
+            one_step()
+    finish_run()
     t1.record()
     barrier(world)
-    launches = lib.dctp_launch_count() - launches0 + (args.steps * len(acts) if step_graph is not None else 0)   # replayed launches are not seen by the host counter
+    launches = lib.dctp_launch_count() - launches0 + (steps * len(live) if step_graph is not None else 0)
     _lib.check(lib.dctp_check(None))
     ms_total = max_over_ranks(t0.elapsed_time(t1), device, world)
-    value = world * B * args.steps / (ms_total / 1e3)
+    out.update(ms_per_step=ms_total / steps, gpu_launches=int(launches), hook_sites=len(session.sites),
+               activation_bytes_per_step=act_bytes, algorithmic_bytes_per_step=alg_bytes_step,
+               hook_path_GBps=alg_bytes_step * steps / (ms_total / 1e3) / 1e9,
+               binding_roofline_frac=sum(roof[i][2] for i in live) * steps / (ms_total / 1e3))
 
-    # ---- per-kernel durations: the same K steps again with an event pair around every launch (the events keep
-    #      consecutive launches from overlapping, so these are isolated launch durations; not part of `value`)
+    # ---- per-launch durations: the same K steps again with an event pair around every launch (isolated launch durations:
+    #      the events keep consecutive launches from overlapping; not part of the timed value)
     session.reset()
-    for step in range(args.steps):
-        for idx, a in enumerate(acts):
-            ev[step][idx][0].record()
-            session.score(idx, a)
-            ev[step][idx][1].record()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in live] for _ in range(steps)]
+    for step in range(steps):
+        for j, i in enumerate(live):
+            ev[step][j][0].record()
+            session.score(i, acts[i])
+            ev[step][j][1].record()
     torch.cuda.synchronize()
     session.reset()
+    per_site_ms = {i: statistics.mean(ev[s][j][0].elapsed_time(ev[s][j][1]) for s in range(steps)) for j, i in enumerate(live)}
 
-    per_site_ms = [statistics.mean(ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(args.steps)) for i in range(len(acts))]
-    hbm_peak, _, peak_kind = measured_peaks()
-    by_kernel = {}
-    for i, name in enumerate(site_kernel):
-        d = by_kernel.setdefault(name, {'launches_per_step': 0, 'ms_per_step': 0.0, 'bytes_per_step': 0})
-        d['launches_per_step'] += 1
-        d['ms_per_step'] += per_site_ms[i]
-        d['bytes_per_step'] += site_bytes[i]
-    for d in by_kernel.values():
-        d['GBps'] = d['bytes_per_step'] / (d['ms_per_step'] / 1e3) / 1e9
-        d['frac_hbm'] = d['GBps'] / hbm_peak
-    dom_name = max(by_kernel, key=lambda k: by_kernel[k]['ms_per_step'])       # dominant = largest share of the step
-    dom = [i for i, name in enumerate(site_kernel) if name == dom_name]
-    dom_ms = by_kernel[dom_name]['ms_per_step']
-    dom_bytes = by_kernel[dom_name]['bytes_per_step']
-    achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(REPO, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            table = json.load(f)
-        prefix = dom_name.split(' ')[0].rstrip('>')           # e.g. score_t_kernel<64,3 matches both load-width variants
-        hits = [v for k, v in table.items() if isinstance(v, dict) and k.startswith(prefix)]
-        if hits:
-            traffic = sum(v['dram_bytes_per_launch'] * v['launches'] for v in hits) / sum(v['launches'] for v in hits)
-    by_shape = {}
-    for i, a in enumerate(acts):
-        key = '%dx%dx%d' % (a.shape[1] if session.sites[i].variant != 'D' else 12, a.shape[2], a.shape[3])
-        d = by_shape.setdefault(key, {'launches': 0, 'ms': 0.0, 'bytes': 0})
-        d['launches'] += 1
-        d['ms'] += per_site_ms[i]
-        d['bytes'] += site_bytes[i]
-    shape_table = {k: {'launches': v['launches'], 'ms': round(v['ms'], 4), 'GBps': round(v['bytes'] / (v['ms'] / 1e3) / 1e9, 1),
-                       'frac_hbm': round(v['bytes'] / (v['ms'] / 1e3) / 1e9 / hbm_peak, 3)} for k, v in by_shape.items()}
+    def table(key_of):
+        groups = {}
+        for i in live:
+            d = groups.setdefault(key_of(i), {'launches_per_step': 0, 'ms_per_step': 0.0, 'bytes_per_step': 0, 'flops_per_step': 0.0,
+                                              'roofline_s': 0.0, 't_hbm': 0.0})
+            d['launches_per_step'] += 1
+            d['ms_per_step'] += per_site_ms[i]
+            d['bytes_per_step'] += roof[i][0]
+            d['flops_per_step'] += roof[i][1]
+            d['roofline_s'] += roof[i][2]
+            d['t_hbm'] += roof[i][0] / (hbm_peak * 1e9)
+        res = {}
+        for k, d in groups.items():
+            sec = d['ms_per_step'] / 1e3
+            bound = 'hbm' if d['t_hbm'] >= d['roofline_s'] * 0.999 else 'tensor'
+            res[k] = {'launches_per_step': d['launches_per_step'], 'ms_per_step': round(d['ms_per_step'], 4),
+                      'bytes_per_step': d['bytes_per_step'], 'GBps': round(d['bytes_per_step'] / sec / 1e9, 1),
+                      'frac_hbm': round(d['bytes_per_step'] / sec / 1e9 / hbm_peak, 3),
+                      'TFLOPs': round(d['flops_per_step'] / sec / 1e12, 1),
+                      'bound': bound, 'frac': round(d['roofline_s'] / sec, 3)}
+        return res
 
-    # ---- end to end: pinned host batch -> H2D -> forward with hooks live -> D2H of the running sums
-    e2e = None
-    if not args.no_e2e:
+    by_kernel = table(lambda i: site_kernel[i])
+    by_shape = table(lambda i: '%dx%dx%d' % (scored[i], acts[i].shape[2], acts[i].shape[3]))
+    out.update(by_kernel=by_kernel, by_shape=by_shape)
+    if by_kernel:
+        dom_name = max(by_kernel, key=lambda k: by_kernel[k]['ms_per_step'])       # dominant = largest share of the step
+        dom = by_kernel[dom_name]
+        sec = dom['ms_per_step'] / 1e3
+        traffic = None
+        tpath = os.path.join(REPO, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tab = json.load(f)
+            prefix = dom_name.split('<')[0]
+            hits = [v for k, v in tab.items() if isinstance(v, dict) and k.startswith(prefix)]
+            if hits:
+                traffic = sum(v['dram_bytes_per_launch'] * v['launches'] for v in hits) / sum(v['launches'] for v in hits)
+        if dom['bound'] == 'hbm':
+            achieved, peak, unit = dom['bytes_per_step'] / sec / 1e9, hbm_peak, 'GB/s'
+        else:
+            achieved, peak, unit = dom['TFLOPs'], tflops, 'TFLOP/s'
+        out['roofline'] = {'bound': dom['bound'], 'achieved': achieved, 'peak': peak, 'unit': unit, 'frac': dom['frac'],
+                           'traffic': traffic, 'peak_kind': peak_kind, 'kernel': dom_name,
+                           'share_of_step': dom['ms_per_step'] / sum(per_site_ms.values()),
+                           'launches_per_step': dom['launches_per_step'], 'bytes_per_step': dom['bytes_per_step'],
+                           'ms_per_step': dom['ms_per_step'], 'passes_charged': PASSES,
+                           'timing': 'CUDA event pair around every launch, over a repeat of the K timed steps on the same stream '
+                                     '(isolated launch durations; bound = slower of 4*H*W bytes at the measured HBM peak and '
+                                     '3 x 2*H*W*(H+W) FLOPs at the measured sustained bf16 peak, per launch)'}
+
+    # ---- end to end: pinned host batch -> H2D -> forward with hooks live -> D2H of the running sums, every step; the run ends
+    #      with the all-reduce, finalise, top-k, D2H of the scores and the .npy files (rank 0)
+    if with_e2e:
         session.reset()
         pinned_out = torch.empty(session.used + 1, dtype=torch.float64).pin_memory()
-        n_e2e_warm = 2
-
         replay = None
 
-        def e2e_steps(n):
-            # every step: H2D of that step's batch from pinned memory (issued one step ahead on a copy stream, as the
-            # package's own `generate.inference` does), forward with all hooks live, D2H of the running sums, sync
-            if replay is not None:
+        def e2e_steps(n, hooks=True):
+            if replay is not None and hooks:
                 for _ in range(n):
-                    replay(host_batch)             # H2D into the graph's input buffer, then one graph launch
+                    replay(host_batch)
                     pinned_out.copy_(session.flat[:session.used + 1], non_blocking=True)
                     torch.cuda.current_stream().synchronize()
                 return
-            for x in device_batches((host_batch for _ in range(n)), device):
+            src = (host_batch for _ in range(n)) if B > 0 else iter(())
+            for x in device_batches(src, device):
                 with torch.no_grad():
                     net(x)
                 pinned_out.copy_(session.flat[:session.used + 1], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
 
         with session:
-            if args.graph:
+            if args.graph and B > 0:
                 replay = session.capture(host_batch.to(device))
-            e2e_steps(n_e2e_warm)
+            e2e_steps(2)
             session.reset()
             barrier(world)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            e2e_steps(args.steps)
+            e2e_steps(steps)
             e2e_scores, _ = finish_run()
             host_scores = e2e_scores.cpu()
+            if rank == 0 and npy_dir is not None:
+                write_score_files(session.split_files(host_scores.numpy()), npy_dir)
             e1.record()
             barrier(world)
-            # forward alone, same loop without hooks, for the breakdown
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1), device, world)
+            ms_e2e = max_over_ranks(e0.elapsed_time(e1), device, world)
+            # the hooks' own share, in line: one more pass with an event pair around every hook launch inside the forward
+            session.reset()
+            pairs = []
+            plain_score = session.score
+
+            def timed_score(idx, t):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                plain_score(idx, t)
+                b.record()
+                pairs.append((a, b))
+            session.score = timed_score
+            e2e_steps(1)
+            session.score = plain_score
+            torch.cuda.synchronize()
+            hooks_ms = sum(a.elapsed_time(b) for a, b in pairs)
+        # the same loop without hooks (accumulator still copied out), for the breakdown
+        session.remove()
+        e2e_steps(1, hooks=False)
+        barrier(world)
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for _ in range(args.steps):
-            with torch.no_grad():
-                net(host_batch.to(device, non_blocking=True))
+        e2e_steps(steps, hooks=False)
         f1.record()
         torch.cuda.synchronize()
-        e2e = {'value': world * B * args.steps / (ms_e2e / 1e3), 'unit': UNIT,
-               'h2d_bytes_per_step': int(host_batch.numel() * 4), 'd2h_bytes_per_step': int(pinned_out.numel() * 8),
-               'ms_per_step': ms_e2e / args.steps, 'forward_only_ms_per_step': f0.elapsed_time(f1) / args.steps,
-               'score_checksum': float(host_scores.double().sum()), 'cuda_graph': bool(args.graph)}
+        ms_fwd = max_over_ranks(f0.elapsed_time(f1), device, world)
+        out['e2e'] = {'ms_per_step': ms_e2e / steps, 'forward_only_ms_per_step': ms_fwd / steps,
+                      'hooks_in_line_ms_per_step': hooks_ms,
+                      'h2d_bytes_per_step': int(host_batch.numel() * 4), 'd2h_bytes_per_step': int(pinned_out.numel() * 8),
+                      'score_checksum': float(host_scores.double().sum()), 'cuda_graph': bool(args.graph),
+                      'includes': 'H2D of every batch from pinned memory, fp32 cuDNN forward with all hooks live, D2H of the running sums every '
+                                  'step; once per run: all-reduce, finalise, top-k, D2H of the scores, np.save of every score file (rank 0)',
+                      'hooks_in_line_how': 'CUDA event pair around every hook launch inside one extra forward pass (not the timed one)'}
+    out['_acts_cpu'] = [acts[i][:4].cpu() for i in live] if (rank == 0 and world == 1 and net_name == args.net and not args.no_cpu_baseline) else None
+    out['_acts'] = acts if out['_acts_cpu'] is not None else None
+    out['_sites'] = session.sites
+    return out
 
-    clocks = sampler.stop() if rank == 0 else None
+
+def run_ours(args):
+    import shutil
+    import tempfile
+    from dct_pruning_b200 import _lib
+    from dct_pruning_b200.generate import rank_slice
+
+    rank, local_rank, world = dist_setup(args)
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    wl = WORKLOADS[args.net]
+    B = args.batch or wl['batch']
+    side = wl['side']
+    torch.backends.cudnn.allow_tf32 = False            # activations fp32-exact, like the reference's
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    lib = _lib.load()
+    _lib.check(lib.dctp_init())
+    steps = args.steps
+    tmp = tempfile.mkdtemp(prefix='dctp_bench_') if rank == 0 else None
+
+    # clocks are sampled from here to the end of the last timed leg: every timed region lies inside the window
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- headline: batch B per GPU (weak scaling: the work per GPU is fixed)
+    main = measure_net(args, args.net, side, B, rank, local_rank, world, device, lib, steps, not args.no_e2e,
+                       npy_dir=os.path.join(tmp, 'weak') if tmp else None)
+    acts_cpu, acts_gpu, sites = main.pop('_acts_cpu'), main.pop('_acts'), main.pop('_sites')
+    value = world * B * steps / (main['ms_per_step'] * steps / 1e3)
+
+    # ---- CPU legs (rank 0, single GPU run only) while the activations are still around
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_hooks_baseline([a[:4].cpu() for a in acts], session.sites, budget_s=12.0)
-        on_gpu = gpu_tensor_reference_baseline(acts, session.sites, budget_s=4.0)
+    if acts_cpu is not None:
+        cpu = cpu_hooks_baseline(acts_cpu, sites, budget_s=12.0)
+        on_gpu = gpu_tensor_reference_baseline(acts_gpu, sites, budget_s=4.0)
         if on_gpu is not None:
             cpu['reference_hook_on_gpu_tensors'] = on_gpu
+    del acts_cpu, acts_gpu
+    torch.cuda.empty_cache()
 
+    # ---- strong scaling: ONE global batch of B images split over the ranks with rank_slice, exactly what the CLI does
+    #      (generate.inference); at one GPU it is the headline run itself
+    strong = None
+    if not args.no_strong:
+        if world == 1:
+            strong = {'global_batch': B, 'batch_per_gpu': B, 'value': value, 'ms_per_step': main['ms_per_step'], 'same_as': 'headline (one GPU)'}
+            if 'e2e' in main:
+                strong['e2e'] = {'value': B / (main['e2e']['ms_per_step'] / 1e3), 'ms_per_step': main['e2e']['ms_per_step']}
+        else:
+            lo, hi = rank_slice(B, rank, world)
+            sres = measure_net(args, args.net, side, hi - lo, rank, local_rank, world, device, lib, steps, not args.no_e2e,
+                               npy_dir=os.path.join(tmp, 'strong') if tmp else None)
+            for k in ('_acts_cpu', '_acts', '_sites'):
+                sres.pop(k)
+            strong = {'global_batch': B, 'batch_per_gpu': hi - lo, 'value': B / (sres['ms_per_step'] / 1e3), 'ms_per_step': sres['ms_per_step'],
+                      'hook_path_GBps_per_gpu': sres['hook_path_GBps'], 'binding_roofline_frac': sres['binding_roofline_frac'],
+                      'by_shape': sres['by_shape']}
+            if 'e2e' in sres:
+                strong['e2e'] = {'value': B / (sres['e2e']['ms_per_step'] / 1e3), 'ms_per_step': sres['e2e']['ms_per_step'],
+                                 'forward_only_ms_per_step': sres['e2e']['forward_only_ms_per_step'],
+                                 'hooks_in_line_ms_per_step': sres['e2e']['hooks_in_line_ms_per_step']}
+            torch.cuda.empty_cache()
+
+    # ---- BASELINE config 5: U^2-Netp at 320x320 (as BASELINE names it) and 288x288 (what the reference's DUTS loader feeds,
+    #      utils/common.py:154-155), batch 12 per GPU (prune_u2netp.py:90)
+    u2 = None
+    if args.net == 'resnet_50' and not args.no_u2netp:
+        u2 = {}
+        for s_side in (320, 288):
+            r = measure_net(args, 'u2netp', s_side, WORKLOADS['u2netp']['batch'], rank, local_rank, world, device, lib, steps,
+                            (not args.no_e2e) and s_side == 320, npy_dir=os.path.join(tmp, 'u2netp%d' % s_side) if tmp else None)
+            for k in ('_acts_cpu', '_acts', '_sites'):
+                r.pop(k)
+            r['value'] = world * r['batch_per_gpu'] / (r['ms_per_step'] / 1e3)
+            r['unit'] = UNIT
+            if 'e2e' in r:
+                r['e2e']['value'] = world * r['batch_per_gpu'] / (r['e2e']['ms_per_step'] / 1e3)
+            r.pop('by_kernel')
+            u2['side%d' % s_side] = r
+            torch.cuda.empty_cache()
+
+    clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
+        hbm_peak, tflops, peak_kind = measured_peaks()
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16x3 split of fp32 on tcgen05 (fp32 accumulate), fp64 cross-image sums', 'data': 'synthetic',
-            'config': {'workload': wl['name'], 'net': args.net, 'batch_per_gpu': B, 'input_side': side, 'limit': args.steps,
-                       'hook_sites': len(acts), 'activation_bytes_per_step': act_bytes, 'algorithmic_bytes_per_step': alg_bytes_step,
-                       'l2': 'inputs (%.1f GB per step) exceed L2; no flush needed' % (act_bytes / 1e9),
-                       'compress_rate': wl['rate'], 'path': args.path, 'cuda_graph': bool(args.graph), 'parallelism': 'batch-sharded x%d, 1 all-reduce per run' % world},
-            'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                         'traffic': traffic, 'peak_kind': peak_kind, 'kernel': dom_name,
-                         'share_of_step': dom_ms / sum(per_site_ms),
-                         'launches_per_step': len(dom), 'bytes_per_step': dom_bytes, 'ms_per_step': dom_ms,
-                         'timing': 'CUDA event pair around every launch, over a repeat of the K timed steps on the same stream '
-                                   '(the events keep consecutive launches from overlapping: isolated launch durations)'},
-            'hook_path_GBps': alg_bytes_step * args.steps / (ms_total / 1e3) / 1e9,
-            'by_kernel': {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in by_kernel.items()},
-            'by_shape': shape_table,
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': main['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16 hi/lo split of fp32 on tcgen05 (fp32 accumulate), fp64 cross-image sums', 'data': 'synthetic',
+            'config': {'workload': wl['name'], 'net': args.net, 'batch_per_gpu': B, 'input_side': side, 'limit': steps,
+                       'hook_sites': main['hook_sites'], 'activation_bytes_per_step': main['activation_bytes_per_step'],
+                       'algorithmic_bytes_per_step': main['algorithmic_bytes_per_step'],
+                       'l2': 'inputs (%.1f GB per step) exceed L2; no flush needed' % (main['activation_bytes_per_step'] / 1e9),
+                       'compress_rate': wl['rate'], 'path': args.path, 'cuda_graph': bool(args.graph),
+                       'parallelism': 'batch-sharded x%d, 1 all-reduce per run' % world,
+                       'peaks': {'hbm_gbs': hbm_peak, 'bf16_tflops_sustained': tflops, 'kind': peak_kind}},
+            'gpu_launches': main['gpu_launches'],
+            'roofline': main.get('roofline'),
+            'hook_path_GBps': main['hook_path_GBps'],
+            'binding_roofline_frac': main['binding_roofline_frac'],
+            'by_kernel': main['by_kernel'], 'by_shape': main['by_shape'],
             'clocks': clocks,
         }
-        if e2e is not None:
-            line['e2e'] = e2e
+        if 'e2e' in main:
+            e = dict(main['e2e'])
+            e['value'] = world * B / (e['ms_per_step'] / 1e3)
+            e['unit'] = UNIT
+            line['e2e'] = e
+        if strong is not None:
+            line['strong'] = strong
+        if u2 is not None:
+            line['u2netp'] = u2
         if cpu is not None:
             line['cpu_baseline'] = cpu
         print(json.dumps(line))
+        shutil.rmtree(tmp, ignore_errors=True)
     from dct_pruning_b200 import dist as ddist
     ddist.shutdown()
 

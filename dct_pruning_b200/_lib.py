@@ -36,6 +36,7 @@ _SIGNATURES = {
     'dctp_path_for': (_c.c_int, [_c.c_int, _c.c_int, _c.c_longlong]),
     'dctp_occupancy': (_c.c_int, [_c.c_int, _c.c_int]),
     'dctp_launch_count': (_c.c_longlong, []),
+    'dctp_last_kernel': (_c.c_char_p, []),
     'dctp_sm_count': (_c.c_int, []),
 }
 EXPORTS = tuple(_SIGNATURES)

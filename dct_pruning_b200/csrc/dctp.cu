@@ -27,6 +27,8 @@ using namespace dctp;
 thread_local char g_err[512] = "";
 std::mutex g_mu;
 
+void note_kernel(const char* fmt, ...);
+
 int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -56,7 +58,7 @@ struct StackBasis {                                                      // per 
     uint8_t *c2_hi = nullptr, *c2_lo = nullptr;                          // stage-2 basis operand images
     uint16_t* table = nullptr;                                           // Bx offsets of a tile's float4 pieces
     int kp = 0, vec = 0, tile_vec = 0;
-    uint32_t table_bytes = 0;
+    uint32_t table_bytes = 0, lbo1 = 0;
 };
 struct KronBasis { uint8_t *hi = nullptr, *lo = nullptr; };             // per N <= 8: C_N (x) C_N as a shared-memory operand image
 struct LargeBasis { uint16_t *hi = nullptr, *lo = nullptr; int NP = 0, NPR = 0; };   // operand image of C_N: [NP/64][NPR][64], see get_large_basis
@@ -68,6 +70,7 @@ struct State {
     size_t smem_per_sm = 0;
     int* status = nullptr;
     long long launches = 0;
+    char last_kernel[160] = "";                       // instantiation the most recent score launch ran (dctp_last_kernel)
     std::map<std::pair<int, int>, UmmaBasis> umma;     // (N, KP)
     std::map<int, SimtBasis> simt;                     // N
     std::map<int, TBasis> tmem;                        // N
@@ -75,6 +78,7 @@ struct State {
     std::map<int, StackBasis> stack;                   // N
     std::map<int, KronBasis> kron;                     // N
     bool kron_on = true;                               // AUTO routes dense sides <= 8 to the Kronecker kernel (DCTP_KRON=0: round-1 kernels)
+    int stack_cfg = 0;                                 // role layout of the stacked-basis kernel (DCTP_STACK_CFG, see stack_kernel_fn)
     bool stack_on = true;                              // AUTO routes dense even sides to the stacked-basis kernel (DCTP_STACK=0: round-1 kernels)
     long long stack_min_bytes = 0;                     // ... for launches of at least this many bytes (DCTP_STACK_MIN_MB)
     void* encode_tiled = nullptr;                      // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link dependency)
@@ -93,6 +97,13 @@ struct State {
     float* hx = nullptr; size_t hx_bytes = 0;
     double* hacc = nullptr; float* hout = nullptr; size_t hc = 0;
 } g;
+
+void note_kernel(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g.last_kernel, sizeof g.last_kernel, fmt, ap);
+    va_end(ap);
+}
 
 // ------------------------------------------------------------------ cosine bases
 inline double dct_coef(int k, int n, int N) {          // orthonormal DCT-II: C_N[k][n]
@@ -239,12 +250,38 @@ int get_stack_basis(int N, StackBasis& out) {
     b.tile_vec = MT * NN / 4;
     const int pieces = b.vec == 4 ? 1 : 2;
     std::vector<uint16_t> tab(static_cast<size_t>(b.tile_vec) * pieces + 8, 0);
-    for (int f = 0; f < b.tile_vec; ++f)
-        for (int pc = 0; pc < pieces; ++pc) {
-            const int e = 4 * f + 2 * pc, m = e / NN, rem = e % NN, h = rem / N, w = rem % N, gI = m / J, set = m % J;
-            const int n = gI * Np + h, k = set * KP + w;
-            tab[static_cast<size_t>(f) * pieces + pc] = static_cast<uint16_t>((k / 8) * S::LBO1 + n * 16 + (k % 8) * 2);
-        }
+    auto fill = [&](uint32_t lbo) {
+        for (int f = 0; f < b.tile_vec; ++f)
+            for (int pc = 0; pc < pieces; ++pc) {
+                const int e = 4 * f + 2 * pc, m = e / NN, rem = e % NN, h = rem / N, w = rem % N, gI = m / J, set = m % J;
+                const int n = gI * Np + h, k = set * KP + w;
+                tab[static_cast<size_t>(f) * pieces + pc] = static_cast<uint16_t>((k / 8) * lbo + n * 16 + (k % 8) * 2);
+            }
+    };
+    // shared-memory wavefronts of the converters' stores (thread t of a warp stores the pieces of vector f0 + t: 8-byte stores
+    // are served per half-warp, 4-byte stores per warp) for a given chunk distance: pick the bank spread with the fewest
+    auto store_wavefronts = [&]() {
+        long long total = 0;
+        const int width = b.vec == 4 ? 2 : 1, lanes = b.vec == 4 ? 16 : 32;      // banks per store, threads per phase
+        for (int f0 = 0; f0 < b.tile_vec; f0 += lanes)
+            for (int pc = 0; pc < pieces; ++pc) {
+                int cnt[32] = {0}, worst = 0;
+                for (int t = 0; t < lanes && f0 + t < b.tile_vec; ++t)
+                    for (int w = 0; w < width; ++w) {
+                        const int bank = (tab[static_cast<size_t>(f0 + t) * pieces + pc] / 4 + w) % 32;
+                        if (++cnt[bank] > worst) worst = cnt[bank];
+                    }
+                total += worst;
+            }
+        return total;
+    };
+    long long best = -1;
+    for (uint32_t u = 0; u < 8; ++u) {
+        fill(2048u + 16u * u);
+        const long long wf = store_wavefronts();
+        if (best < 0 || wf < best) { best = wf; b.lbo1 = 2048u + 16u * u; }
+    }
+    fill(b.lbo1);
     b.table_bytes = static_cast<uint32_t>((static_cast<size_t>(b.tile_vec) * pieces * 2 + 15) / 16 * 16);
     if (b.table_bytes > S::TABLE_MAX) return fail(DCTP_E_UNSUPPORTED, "stacked-basis kernel: offset table of side %d does not fit", N);
     CUDA_TRY(cudaMalloc(&b.a_img, img.size() * 4));
@@ -259,6 +296,33 @@ int get_stack_basis(int N, StackBasis& out) {
     out = b;
     return DCTP_OK;
 }
+
+// instantiations: variant v = (KP 16, VEC 4), (16, 2), (32, 4), (32, 2), (48, 4), (64, 4); configuration cfg = role layout
+//   cfg 0 (default): 8 converter warps in two groups (alternate tiles), one epilogue-1 group, 23 warps
+//   cfg 1: the same with two epilogue-1 groups, 31 warps            cfg 2: 4 converter warps in one group, 19 warps
+// measured on B200, [256,C,N,N] 56x56 / 28x28 / 14x14, TB/s: cfg 0 3.85 / 3.67 / 3.26, cfg 1 3.78 / 3.57 / 3.12, cfg 2 3.59 / 3.31 / 2.89
+constexpr int STACK_CFGS = 3;
+typedef void (*StackKernel)(const CUtensorMap, const StackArgs);
+template <int NCONV, int NE1G, int NCG>
+StackKernel stack_kernel_of(int v) {
+    switch (v) {
+        case 0: return score_stack_kernel<16, 4, NCONV, NE1G, NCG>;
+        case 1: return score_stack_kernel<16, 2, NCONV, NE1G, NCG>;
+        case 2: return score_stack_kernel<32, 4, NCONV, NE1G, NCG>;
+        case 3: return score_stack_kernel<32, 2, NCONV, NE1G, NCG>;
+        case 4: return score_stack_kernel<48, 4, NCONV, NE1G, NCG>;
+        default: return score_stack_kernel<64, 4, NCONV, NE1G, NCG>;
+    }
+}
+StackKernel stack_kernel_fn(int cfg, int v) {
+    switch (cfg) {
+        case 1: return stack_kernel_of<8, 2, 2>(v);
+        case 2: return stack_kernel_of<4, 1, 1>(v);
+        default: return stack_kernel_of<8, 1, 2>(v);
+    }
+}
+const void* stack_kernel_ptr(int cfg, int v) { return reinterpret_cast<const void*>(stack_kernel_fn(cfg, v)); }
+int stack_threads(int cfg) { return cfg == 1 ? (8 + 16 + 7) * 32 : cfg == 2 ? (4 + 8 + 7) * 32 : (8 + 8 + 7) * 32; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -283,6 +347,7 @@ int launch_stack(const float* first, int B, int N, int c_count, double* accum, f
     a.tail_tile = (a.total_elems % 32) != 0 ? a.num_tiles - 1 : -1;
     a.idesc1 = umma::make_idesc_bf16(128, a.ncols, false, false);
     a.idesc2 = umma::make_idesc_bf16(128, KP, false, false);
+    a.lbo1 = basis.lbo1;
     a.a_img = basis.a_img; a.c2_hi = basis.c2_hi; a.c2_lo = basis.c2_lo; a.table = basis.table; a.table_bytes = basis.table_bytes;
     a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
     CUtensorMap map;
@@ -298,15 +363,29 @@ int launch_stack(const float* first, int B, int N, int c_count, double* accum, f
         if (r != CUDA_SUCCESS) return fail(DCTP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %lld rows, box %d", (int)r, rows, a.tile_rows);
     }
     int grid = g.sm_count < a.num_tiles ? g.sm_count : a.num_tiles;
+    a.chan_step = static_cast<int>((static_cast<long long>(grid) * a.MT) % c_count);
     const size_t smem = StackSmem::TOTAL;
     const bool v4 = basis.vec == 4;
-    switch (KP) {
-        case 16: CUDA_TRY(v4 ? launch_score_tma(score_stack_kernel<16, 4>, grid, STACK_NT, smem, stream, map, a)
-                             : launch_score_tma(score_stack_kernel<16, 2>, grid, STACK_NT, smem, stream, map, a)); break;
-        case 32: CUDA_TRY(v4 ? launch_score_tma(score_stack_kernel<32, 4>, grid, STACK_NT, smem, stream, map, a)
-                             : launch_score_tma(score_stack_kernel<32, 2>, grid, STACK_NT, smem, stream, map, a)); break;
-        case 48: CUDA_TRY(launch_score_tma(score_stack_kernel<48, 4>, grid, STACK_NT, smem, stream, map, a)); break;
-        default: CUDA_TRY(launch_score_tma(score_stack_kernel<64, 4>, grid, STACK_NT, smem, stream, map, a)); break;
+    static long long* trace_buf = nullptr;
+    const bool tracing = std::getenv("DCTP_S_TRACE") != nullptr;
+    if (tracing) {
+        if (!trace_buf) CUDA_TRY(cudaMalloc(&trace_buf, 64 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(trace_buf, 0, 64 * sizeof(long long)));
+        a.trace = trace_buf;
+    }
+    const int variant = KP == 16 ? (v4 ? 0 : 1) : KP == 32 ? (v4 ? 2 : 3) : KP == 48 ? 4 : 5;
+    CUDA_TRY(launch_score_tma(stack_kernel_fn(g.stack_cfg, variant), grid, stack_threads(g.stack_cfg), smem, stream, map, a));
+    note_kernel("score_stack_kernel<KP=%d,VEC=%d,cfg%d> (tcgen05, stacked hi/lo basis in TMEM, TMA tile ring, warp specialised)", KP, basis.vec, g.stack_cfg);
+    if (tracing) {
+        long long h[64];
+        CUDA_TRY(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
+        const double n = h[14] > 0 ? double(h[14]) : 1.0;
+        fprintf(stderr, "[dctp trace] stack N=%d cfg %d, CTA 0, %lld tiles, cycles per tile | producer: wait slot %.0f | converter: wait Bx free %.0f, "
+                        "wait TMA %.0f, convert %.0f, fence+arrive %.0f | issuer 1: wait Bx %.0f, wait D1 free %.0f, issue %.0f | issuer 2: wait A2 %.0f, "
+                        "wait D2 free %.0f, issue %.0f | epi1 (first group, per tile of the CTA): wait D1 %.0f, wait A2 free %.0f, work %.0f | "
+                        "epi2: wait D2 %.0f, TMEM loads %.0f, sums+shuffles %.0f, atomics %.0f\n",
+                N, g.stack_cfg, h[14], h[0] / n, h[16] / n, h[17] / n, h[18] / n, h[19] / n, h[8] / n, h[9] / n, h[10] / n, h[40] / n, h[41] / n,
+                h[42] / n, h[24] / n, h[25] / n, h[26] / n, h[32] / n, h[34] / n, h[35] / n, h[33] / n);
     }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
@@ -400,6 +479,7 @@ int launch_kron(const float* first, int B, int N, int c_count, double* accum, fl
         default: KRON_LAUNCH(64); break;
     }
 #undef KRON_LAUNCH
+    note_kernel("score_kron_kernel<K2=%d,%s> (tcgen05, single-stage Kronecker, TMA tile ring, warp specialised)", K2, even ? "even" : "odd");
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     return DCTP_OK;
@@ -526,7 +606,14 @@ int setup_umma_all(int (*regs)[2]) {
 }
 
 int ensure_init() {
-    if (g.ready) return DCTP_OK;
+    if (g.ready) {                                       // bases, status word and kernel attributes belong to the device of the first call
+        int cur = -1;
+        CUDA_TRY(cudaGetDevice(&cur));
+        if (cur != g.device)
+            return fail(DCTP_E_INVALID, "libdctp was initialised on device %d; the current device is %d (one device per process: launch one "
+                                        "process per GPU, or dctp_shutdown() before switching)", g.device, cur);
+        return DCTP_OK;
+    }
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     cudaDeviceProp prop;
@@ -550,13 +637,12 @@ int ensure_init() {
         }
     }
     {
-        const void* fns[] = {reinterpret_cast<const void*>(score_stack_kernel<16, 4>), reinterpret_cast<const void*>(score_stack_kernel<16, 2>),
-                             reinterpret_cast<const void*>(score_stack_kernel<32, 4>), reinterpret_cast<const void*>(score_stack_kernel<32, 2>),
-                             reinterpret_cast<const void*>(score_stack_kernel<48, 4>), reinterpret_cast<const void*>(score_stack_kernel<64, 4>)};
-        for (const void* fn : fns) {
-            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(StackSmem::TOTAL)));
-            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        }
+        for (int cfg = 0; cfg < STACK_CFGS; ++cfg)
+            for (int v = 0; v < 6; ++v) {
+                const void* fn = stack_kernel_ptr(cfg, v);
+                CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(StackSmem::TOTAL)));
+                CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            }
         const void* kfns[] = {reinterpret_cast<const void*>(score_kron_kernel<16, true>), reinterpret_cast<const void*>(score_kron_kernel<16, false>),
                               reinterpret_cast<const void*>(score_kron_kernel<32, true>), reinterpret_cast<const void*>(score_kron_kernel<32, false>),
                               reinterpret_cast<const void*>(score_kron_kernel<48, true>), reinterpret_cast<const void*>(score_kron_kernel<48, false>),
@@ -570,6 +656,7 @@ int ensure_init() {
         if (!g.encode_tiled) return fail(DCTP_E_CUDA, "the driver does not export cuTensorMapEncodeTiled");
     }
     if (const char* e = std::getenv("DCTP_KRON")) g.kron_on = std::atoi(e) != 0;
+    if (const char* e = std::getenv("DCTP_STACK_CFG")) { g.stack_cfg = std::atoi(e); if (g.stack_cfg < 0 || g.stack_cfg >= STACK_CFGS) g.stack_cfg = 0; }
     if (const char* e = std::getenv("DCTP_STACK")) g.stack_on = std::atoi(e) != 0;
     if (const char* e = std::getenv("DCTP_STACK_MIN_MB")) g.stack_min_bytes = static_cast<long long>(std::atoi(e)) << 20;
     if (const char* e = std::getenv("DCTP_TP")) g.t_prod = std::atoi(e) != 0;
@@ -632,6 +719,7 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
         a.trace = trace_buf;
     }
     CUDA_TRY(launch_score(score_large_kernel, grid, LARGE_NT, LargeSmem::TOTAL, stream, a));
+    note_kernel("score_large_kernel (tcgen05, tiled two-stage, 18 warps)");
     if (tracing) {
         long long h[16];
         CUDA_TRY(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
@@ -722,6 +810,8 @@ int launch_t(const float* first, int B, int N, int c_count, double* accum, float
         else if (v2) CUDA_TRY(launch_score(score_t_kernel<32, 6, 2>, grid, 768, smem, stream, a));
         else CUDA_TRY(launch_score(score_t_kernel<32, 6, 1>, grid, 768, smem, stream, a));
     }
+    note_kernel("score_t_kernel<%d,%d,VPE=%d%s> (tcgen05, block-diagonal basis in TMEM)", n1max, ns, basis.vpe,
+                (n1max == 64 && g.t_prod && basis.tile_vec <= 13 * 128 && !v2) ? ",2 producer warpgroups" : "");
     if (tracing) {
         long long h[256];
         CUDA_TRY(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
@@ -814,6 +904,7 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
         case LOAD_GEN2: CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_GEN2, false>, grid, 128, smem, stream, a)); break;
         default: CUDA_TRY(launch_score(score_umma_kernel<KP, LOAD_GEN1, false>, grid, 128, smem, stream, a)); break;
     }
+    note_kernel("score_umma_kernel<%d,%d,%d> (tcgen05 bf16x3, operands in shared memory)", KP, mode, pf ? 1 : 0);
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     return DCTP_OK;
@@ -835,6 +926,7 @@ int launch_simt(const float* x, int B, int H, int W, long long stride_b, long lo
         int grid = g.sm_count * 2;
         if (grid > tiles) grid = tiles;
         score_simt_small_kernel<<<grid, 256, SIMT_SMALL_SMEM, stream>>>(a);
+        note_kernel("score_simt_small_kernel (fp32 CUDA cores)");
     } else {
         const int Hpad = (H + SIMT_T - 1) / SIMT_T * SIMT_T;
         const size_t smem = static_cast<size_t>(Hpad + 2 * SIMT_T) * SIMT_LD * sizeof(float);
@@ -842,6 +934,7 @@ int launch_simt(const float* x, int B, int H, int W, long long stride_b, long lo
         if (energy_out) CUDA_TRY(cudaMemsetAsync(energy_out, 0, sizeof(float) * a.n_maps, stream));
         const unsigned grid = static_cast<unsigned>((W + SIMT_T - 1) / SIMT_T) * static_cast<unsigned>(a.n_maps);
         score_simt_large_kernel<<<grid, 256, smem, stream>>>(a);
+        note_kernel("score_simt_large_kernel (fp32 CUDA cores)");
     }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
@@ -893,6 +986,7 @@ int dctp_sm_count(void) {
     return rc ? rc : g.sm_count;
 }
 long long dctp_launch_count(void) { return g.launches; }
+const char* dctp_last_kernel(void) { return g.last_kernel; }
 
 int dctp_path_for(int H, int W, long long stride_h) { return resolve_path(DCTP_PATH_AUTO, H, W, stride_h); }
 

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
                 if (lane == 0) mbar_arrive(d_free + sl);
                 if (m < a.n_maps) {
                     const float e = e0 + e1;
-                    atomicAdd(a.accum + (m % a.c_count), static_cast<double>(e));
+                    atomicAdd(a.accum + (static_cast<uint32_t>(m) % static_cast<uint32_t>(a.c_count)), static_cast<double>(e));
                     if (a.energy_out) a.energy_out[m] = e;
                 }
             }

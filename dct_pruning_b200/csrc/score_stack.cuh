@@ -25,13 +25,14 @@
 // Tensor-core time per 25 KB of input: 448 + 384 cycles at 56x56 (score_tmem.cuh: 672 + 384), 512 + 192 at 28x28,
 // 512 + 96 at 14x14, against 1113 cycles of HBM time at the measured 6.55 TB/s.
 //
-// The kernel is warp specialised (one CTA per SM, 18 warps), every hand-over is an mbarrier:
-//   warp 16     TMA producer: one cp.async.bulk.tensor.2d per tile (tensor map over the dense fp32 stream viewed as
+// The kernel is warp specialised (one CTA per SM), every hand-over is an mbarrier.  Roles, in warp order:
+//   converters  NCONV warps: fp32 tile -> bf16 hi/lo -> Bx (two buffers), offsets from a host-built table
+//   epilogue 1  NE1G groups of 8 warps (warp = lane quarter q x row slot s); group g takes the CTA's tiles g, g + NE1G, ...
+//   epilogue 2  4 warps
+//   producer    1 warp (one thread): one cp.async.bulk.tensor.2d per tile (tensor map over the dense fp32 stream viewed as
 //               [rows, 32 floats]; a tile is a box of tile_rows rows; rows past the end arrive as zeros) into a ring of 3
-//   warps 0-3   converters: fp32 tile -> bf16 hi/lo -> Bx (two buffers), offsets from a host-built table
-//   warp 17     MMA issuer (one thread): stage 1 of tile i, then stage 2 of tile i-1
-//   warps 4-11  epilogue 1 (warp = lane quarter q x row slot s)
-//   warps 12-15 epilogue 2
+//   issuers     2 warps (one thread each): stage 1 and stage 2 have their own issuing thread, so that neither the waits nor
+//               the ~25 cycles it takes to issue an MMA of one stage hold up the other
 // TMEM (512 columns): A 32 | D1 2 x 128 | A2 2 x 64 | D2 NB2 x 64 (NB2 = 1: 480 columns in use).
 #pragma once
 #include <cuda.h>
@@ -47,8 +48,10 @@ struct StackArgs {
     int G, MT;                      // maps per set and per tile (MT = G * J)
     int ncols;                      // G * Np = MMA N of stage 1
     int tile_elems, tile_rows, tile_vec, num_tiles;
+    int chan_step;                  // (gridDim.x * MT) mod c_count: channel advance between a CTA's consecutive tiles
     int tail_tile;                  // tile converted straight from global memory (the stream does not end on a 128-byte row), or -1
     uint32_t idesc1, idesc2;
+    uint32_t lbo1;                  // Bx: byte distance between consecutive 8-element k-chunks (2048 + 16 u, u chosen per side for conflict-free stores)
     const uint32_t* a_img;          // [128][32] packed bf16 pairs: the stacked basis as it sits in TMEM
     const uint8_t* c2_hi;           // stage-2 basis as a shared-memory operand image (hi, lo): C2_HALF bytes each
     const uint8_t* c2_lo;
@@ -58,12 +61,13 @@ struct StackArgs {
     float* energy_out;
     float* dump;
     int* status;
+    long long* trace;               // bring-up aid (DCTP_S_TRACE): per role of CTA 0, cycles spent waiting / working
 };
 
 struct StackSmem {
     static constexpr uint32_t NSTG = 3, STG_STRIDE = 32768;              // TMA ring: fp32 tiles of at most 32 KB
-    static constexpr uint32_t LBO1 = 128 * 16 + 16;                      // Bx: k-chunk c of row n at c * LBO1 + n * 16 (+16: bank spread)
-    static constexpr uint32_t BX_HALF = 8 * LBO1;                        // 16512
+    static constexpr uint32_t LBO1_MAX = 128 * 16 + 16 * 7;              // Bx: k-chunk c of row n at c * lbo1 + n * 16; lbo1 = 2048 + 16 u spreads the banks
+    static constexpr uint32_t BX_HALF = 8 * LBO1_MAX;                    // 17280
     static constexpr uint32_t LBO2 = 64 * 16 + 16;                       // stage-2 basis, same layout
     static constexpr uint32_t C2_HALF = 8 * LBO2;                        // 8320
     static constexpr uint32_t OFF_BX = NSTG * STG_STRIDE;
@@ -76,18 +80,27 @@ struct StackSmem {
     static constexpr uint32_t TOTAL = OFF_SLOT + 128;
 };
 
-constexpr int STACK_NT = 576;
 
 // KP: contraction length per map (N rounded up to 16); VEC: granularity of a row in the fp32 stream (4: N % 4 == 0, 2: N even)
-template <int KP, int VEC>
-__global__ void __launch_bounds__(STACK_NT, 1) score_stack_kernel(const __grid_constant__ CUtensorMap tmap, const StackArgs a) {
+// NCONV: converter warps (4 or 8) in NCG groups (group g converts the CTA's tiles g, g + NCG, ...); NE1G: epilogue-1 groups (1 or 2).
+// Every warp polls the mbarriers it depends on itself.  (Measured and dropped: one polling warp per role releasing its siblings
+// through a named barrier - the polls cost issue slots, the sleep behind mbarrier.try_wait being woken by any barrier event of
+// the CTA, but the extra hop costs more: 56x56 3.17 against 3.49 TB/s.)
+template <int KP, int VEC, int NCONV, int NE1G, int NCG>
+__global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_kernel(const __grid_constant__ CUtensorMap tmap, const StackArgs a) {
     using S = StackSmem;
     using namespace umma;
     constexpr int J = KP <= 32 ? 64 / KP : 1;
     constexpr int K1S = J * KP / 16, K2S = KP / 16;
     constexpr int G = KP == 16 ? 8 : KP == 32 ? 4 : 2, T2 = G / 2;
-    constexpr uint32_t TM_A = 0, TM_D1 = 32, TM_A2 = 288, TM_D2 = 416;   // TMEM columns (D1, A2 double buffered)
-    constexpr uint32_t STEP1 = (2 * S::LBO1) >> 4, STEP2 = (2 * S::LBO2) >> 4;   // one k-step (two 8-element chunks) in descriptor units
+    constexpr uint32_t W_E1 = NCONV, W_E2 = NCONV + 8 * NE1G, W_PROD = W_E2 + 4, W_MMA = W_PROD + 1, W_MMA2 = W_PROD + 2, NT = (W_MMA2 + 1) * 32;
+    constexpr uint32_t NCT = NCONV * 32 / NCG;                            // threads that convert one tile
+    constexpr uint32_t TM_A = 0, TM_D1 = 32;                              // TMEM columns: A | D1 x 2 | A2 x 2 (64 each) | D2 x NB2 (64 each)
+    const uint32_t d1_stride = a.ncols <= 112 ? 112u : 128u;
+    const uint32_t TM_A2 = TM_D1 + 2 * d1_stride, TM_D2 = TM_A2 + 128;
+    const uint32_t nb2 = TM_D2 + 128 <= 512 ? 2u : 1u;                    // a second D2 buffer when D1 is at most 112 columns wide
+    const uint32_t STEP1 = (2 * a.lbo1) >> 4;                             // one k-step (two 8-element chunks) in descriptor units
+    constexpr uint32_t STEP2 = (2 * S::LBO2) >> 4;
 
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,38 +110,38 @@ __global__ void __launch_bounds__(STACK_NT, 1) score_stack_kernel(const __grid_c
     const uint8_t* tab = smem + S::OFF_TABLE;
     float* red = reinterpret_cast<float*>(smem + S::OFF_RED);             // [parity][q][8]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);
-    uint64_t* stg_full = bars;                                            // TMA landed (tx bytes)
-    uint64_t* stg_free = bars + 3;                                        // 4 converter warps
-    uint64_t* bx_full = bars + 6;                                         // 4 converter warps
-    uint64_t* bx_free = bars + 8;                                         // stage-1 MMAs of the buffer have completed
-    uint64_t* d1_full = bars + 10;                                        // ... and D1 is complete
-    uint64_t* d1_free = bars + 12;                                        // 8 epilogue-1 warps have read it
-    uint64_t* a2_full = bars + 14;                                        // 8 epilogue-1 warps have written A2
-    uint64_t* a2_free = bars + 16;                                        // stage-2 MMAs have read it
-    uint64_t* d2_full = bars + 18;
-    uint64_t* d2_free = bars + 19;                                        // 4 epilogue-2 warps
+    uint64_t* stg_full = bars;                                            // [3] TMA landed (tx bytes)
+    uint64_t* stg_free = bars + 3;                                        // [3] NCONV converter warps
+    uint64_t* bx_full = bars + 6;                                         // [2] NCONV converter warps
+    uint64_t* bx_free = bars + 8;                                         // [2] stage-1 MMAs of the buffer have completed
+    uint64_t* d1_full = bars + 10;                                        // [2] ... and D1 is complete
+    uint64_t* d1_free = bars + 12;                                        // [2] 8 epilogue-1 warps have read it
+    uint64_t* a2_full = bars + 14;                                        // [2] 8 epilogue-1 warps have written A2
+    uint64_t* a2_free = bars + 16;                                        // [2] stage-2 MMAs have read it
+    uint64_t* d2_full = bars + 18;                                        // [2]
+    uint64_t* d2_free = bars + 20;                                        // [2] 4 epilogue-2 warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_SLOT);
 
     // ---- prologue (independent of the activation: overlaps the preceding kernel under a dependent launch)
-    for (uint32_t off = tid * 16; off < 4 * S::BX_HALF; off += STACK_NT * 16) *reinterpret_cast<uint4*>(bx + off) = make_uint4(0, 0, 0, 0);
-    for (uint32_t off = tid * 16; off < S::C2_HALF; off += STACK_NT * 16) {
+    for (uint32_t off = tid * 16; off < 4 * S::BX_HALF; off += NT * 16) *reinterpret_cast<uint4*>(bx + off) = make_uint4(0, 0, 0, 0);
+    for (uint32_t off = tid * 16; off < S::C2_HALF; off += NT * 16) {
         *reinterpret_cast<uint4*>(c2 + off) = *reinterpret_cast<const uint4*>(a.c2_hi + off);
         *reinterpret_cast<uint4*>(c2 + S::C2_HALF + off) = *reinterpret_cast<const uint4*>(a.c2_lo + off);
     }
-    for (uint32_t off = tid * 16; off < a.table_bytes; off += STACK_NT * 16)
+    for (uint32_t off = tid * 16; off < a.table_bytes; off += NT * 16)
         *reinterpret_cast<uint4*>(smem + S::OFF_TABLE + off) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.table) + off);
-    if (warp == 17) tmem_alloc<512>(tmem_slot);
+    if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        for (int s = 0; s < 3; ++s) { mbar_init(stg_full + s, 1); mbar_init(stg_free + s, 4); }
+        for (int s = 0; s < 3; ++s) { mbar_init(stg_full + s, 1); mbar_init(stg_free + s, NCONV / NCG); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bx_full + b, 4); mbar_init(bx_free + b, 1);
+            mbar_init(bx_full + b, NCONV / NCG); mbar_init(bx_free + b, 1);
             mbar_init(d1_full + b, 1); mbar_init(d1_free + b, 8);
             mbar_init(a2_full + b, 8); mbar_init(a2_free + b, 1);
+            mbar_init(d2_full + b, 1); mbar_init(d2_free + b, 4);
         }
-        mbar_init(d2_full, 1); mbar_init(d2_free, 4);
         mbar_init_fence();
     }
-    if (warp == 16 && lane == 0) tma_prefetch_desc(&tmap);
+    if (warp == W_PROD && lane == 0) tma_prefetch_desc(&tmap);
     fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -165,60 +178,47 @@ __global__ void __launch_bounds__(STACK_NT, 1) score_stack_kernel(const __grid_c
     const int first = blockIdx.x, stride = gridDim.x;
     const uint32_t tile_bytes = static_cast<uint32_t>(a.tile_rows) * 128u;
     bool dead = false;
-#define STACK_WAIT(bar, par)                         \
-    if (!mbar_wait((bar), (par))) {                  \
-        dead = true;                                 \
-        break;                                       \
-    }
-
-    if (warp == 16) {
+    // bring-up trace: one thread per role accumulates cycles in registers and writes them when its loop ends
+    const bool tr_on = a.trace != nullptr && blockIdx.x == 0;
+    bool tr_me = false;
+    long long tr_mark = 0, tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0, tr5 = 0;
+#define TR_START() do { if (tr_me) tr_mark = clock64(); } while (0)
+#define TR_ADD(acc) do { if (tr_me) { const long long now_ = clock64(); (acc) += now_ - tr_mark; tr_mark = now_; } } while (0)
+#define TR_FLUSH(base) do { if (tr_me) { a.trace[(base)] = tr0; a.trace[(base) + 1] = tr1; a.trace[(base) + 2] = tr2; a.trace[(base) + 3] = tr3; \
+                                         a.trace[(base) + 4] = tr4; a.trace[(base) + 5] = tr5; } } while (0)
+    if (warp == W_PROD) {
         // ================================================================ TMA producer
         if (elect_one()) {
+            tr_me = tr_on;
             uint32_t it = 0;
             for (int tile = first; tile < a.num_tiles; tile += stride) {
                 if (tile == a.tail_tile) continue;
                 const uint32_t s = it % S::NSTG;
-                if (it >= S::NSTG) STACK_WAIT(stg_free + s, ((it / S::NSTG) - 1u) & 1u);
+                TR_START();
+                if (it >= S::NSTG && !mbar_wait(stg_free + s, ((it / S::NSTG) - 1u) & 1u)) { dead = true; break; }
+                TR_ADD(tr0);
                 mbar_arrive_expect_tx(stg_full + s, tile_bytes);
                 tma_load_2d(stg + s * S::STG_STRIDE, &tmap, 0, tile * a.tile_rows, stg_full + s);
                 ++it;
             }
+            TR_FLUSH(0);
         }
         __syncwarp();
-    } else if (warp == 17) {
-        // ================================================================ MMA issuer
+    } else if (warp == W_MMA) {
+        // ================================================================ MMA issuer, stage 1: D1 = A * Bx^T (Bx_hi, then Bx_lo)
         if (elect_one()) {
-            const uint64_t desc = make_smem_desc(0, S::LBO1, 128, SWIZZLE_NONE);
-            const uint64_t desc2 = make_smem_desc(0, S::LBO2, 128, SWIZZLE_NONE);
-            const uint32_t lo_c2_hi = static_cast<uint32_t>(desc2) + (smem_u32(c2) >> 4);
-            const uint32_t lo_c2_lo = lo_c2_hi + (S::C2_HALF >> 4);
-            auto stage2 = [&](uint32_t m) -> bool {                       // tile number m of this CTA
-                const uint32_t b = m & 1u;
-                if (!mbar_wait(a2_full + b, (m >> 1) & 1u)) return false;
-                if (m >= 1 && !mbar_wait(d2_free, (m - 1u) & 1u)) return false;
-                tc_fence_after_sync();
-#pragma unroll
-                for (int t = 0; t < T2; ++t) {
-                    const uint32_t d = tmem + TM_D2 + t * KP;
-                    const uint32_t ahi = tmem + TM_A2 + b * 64 + t * KP, alo = ahi + KP / 2;
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass)
-#pragma unroll
-                        for (int ks = 0; ks < K2S; ++ks)
-                            mma_bf16_ts(d, (pass == 1 ? alo : ahi) + 8 * ks,
-                                        desc_with_lo(desc2, (pass == 2 ? lo_c2_lo : lo_c2_hi) + ks * STEP2), a.idesc2, (pass | ks) != 0);
-                }
-                mma_commit(d2_full);
-                mma_commit(a2_free + b);
-                return true;
-            };
+            tr_me = tr_on;
+            const uint64_t desc = make_smem_desc(0, a.lbo1, 128, SWIZZLE_NONE);
             uint32_t n = 0;
             for (int tile = first; tile < a.num_tiles; tile += stride, ++n) {
                 const uint32_t b = n & 1u;
-                STACK_WAIT(bx_full + b, (n >> 1) & 1u);
-                if (n >= 2) STACK_WAIT(d1_free + b, ((n >> 1) - 1u) & 1u);
+                TR_START();
+                if (!mbar_wait(bx_full + b, (n >> 1) & 1u)) { dead = true; break; }
+                TR_ADD(tr0);
+                if (n >= 2 && !mbar_wait(d1_free + b, ((n >> 1) - 1u) & 1u)) { dead = true; break; }
+                TR_ADD(tr1);
                 tc_fence_after_sync();
-                const uint32_t d1 = tmem + TM_D1 + b * 128;
+                const uint32_t d1 = tmem + TM_D1 + b * d1_stride;
                 const uint32_t lo_hi = static_cast<uint32_t>(desc) + (smem_u32(bx + b * 2 * S::BX_HALF) >> 4);
                 const uint32_t lo_lo = lo_hi + (S::BX_HALF >> 4);
 #pragma unroll
@@ -229,176 +229,347 @@ __global__ void __launch_bounds__(STACK_NT, 1) score_stack_kernel(const __grid_c
                                     (pass | ks) != 0);
                 mma_commit(d1_full + b);
                 mma_commit(bx_free + b);
-                if (n >= 1 && !stage2(n - 1)) { dead = true; break; }
+                TR_ADD(tr2);
             }
-            if (!dead && n >= 1 && !stage2(n - 1)) dead = true;
+            TR_FLUSH(8);
+            if (tr_me) a.trace[14] = n;
         }
         __syncwarp();
-    } else if (warp < 4) {
+    } else if (warp == W_MMA2) {
+        // ================================================================ MMA issuer, stage 2: D2 = A2 * C^T (hi*hi + lo*hi + hi*lo)
+        if (elect_one()) {
+            tr_me = tr_on;
+            const uint64_t desc2 = make_smem_desc(0, S::LBO2, 128, SWIZZLE_NONE);
+            const uint32_t lo_c2_hi = static_cast<uint32_t>(desc2) + (smem_u32(c2) >> 4);
+            const uint32_t lo_c2_lo = lo_c2_hi + (S::C2_HALF >> 4);
+            uint32_t m = 0;
+            for (int tile = first; tile < a.num_tiles; tile += stride, ++m) {
+                const uint32_t b = m & 1u;
+                TR_START();
+                if (!mbar_wait(a2_full + b, (m >> 1) & 1u)) { dead = true; break; }
+                TR_ADD(tr0);
+                const uint32_t b2 = nb2 == 2 ? b : 0u, use2 = nb2 == 2 ? (m >> 1) : m;      // D2 buffer and how often it has been filled
+                if (use2 >= 1 && !mbar_wait(d2_free + b2, (use2 - 1u) & 1u)) { dead = true; break; }
+                TR_ADD(tr1);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int t = 0; t < T2; ++t) {
+                    const uint32_t d = tmem + TM_D2 + b2 * 64 + t * KP;
+                    const uint32_t ahi = tmem + TM_A2 + b * 64 + t * KP, alo = ahi + KP / 2;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+                        for (int ks = 0; ks < K2S; ++ks)
+                            mma_bf16_ts(d, (pass == 1 ? alo : ahi) + 8 * ks,
+                                        desc_with_lo(desc2, (pass == 2 ? lo_c2_lo : lo_c2_hi) + ks * STEP2), a.idesc2, (pass | ks) != 0);
+                }
+                mma_commit(d2_full + b2);
+                mma_commit(a2_free + b);
+                TR_ADD(tr2);
+            }
+            TR_FLUSH(40);
+        }
+        __syncwarp();
+    } else if (warp < W_E1) {
         // ================================================================ converters: fp32 tile -> bf16 hi/lo -> Bx
-        uint32_t it = 0, n = 0;
-        for (int tile = first; tile < a.num_tiles; tile += stride, ++n) {
-            const uint32_t b = n & 1u;
-            if (n >= 2) STACK_WAIT(bx_free + b, ((n >> 1) - 1u) & 1u);
+        const uint32_t cg = warp / (NCONV / NCG), ctid = tid - cg * NCT;     // converter group, thread within it
+        uint32_t n = cg;                                                   // this CTA's tile number (= its TMA sequence number: only the
+        tr_me = tr_on && tid == 0;                                         //  CTA's last tile can be the one converted from global memory)
+        for (int tile = first + (int)cg * stride; tile < a.num_tiles; tile += NCG * stride, n += NCG) {
+            const uint32_t b = n & 1u, s = n % S::NSTG, it = n;
+            TR_START();
+            {
+                bool ok = true;
+                if (n >= 2) ok = mbar_wait(bx_free + b, ((n >> 1) - 1u) & 1u);
+                TR_ADD(tr0);
+                if (ok && tile != a.tail_tile) ok = mbar_wait(stg_full + s, (it / S::NSTG) & 1u);
+                TR_ADD(tr1);
+                if (!ok) { dead = true; break; }
+            }
             uint8_t* hi = bx + b * 2 * S::BX_HALF;
             uint8_t* lo = hi + S::BX_HALF;
-            auto emit = [&](int f, const float4 v) {
+            auto emit = [&](uint32_t o, const float4 v) {                  // o: table entry of the vector
                 uint32_t h0, l0, h1, l1;
                 split2(v.x, v.y, h0, l0);
                 split2(v.z, v.w, h1, l1);
                 if constexpr (VEC == 4) {
-                    const uint32_t off = reinterpret_cast<const uint16_t*>(tab)[f];
-                    *reinterpret_cast<uint2*>(hi + off) = make_uint2(h0, h1);
-                    *reinterpret_cast<uint2*>(lo + off) = make_uint2(l0, l1);
+                    *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2*>(lo + o) = make_uint2(l0, l1);
                 } else {
-                    const uint32_t o2 = reinterpret_cast<const uint32_t*>(tab)[f];
-                    const uint32_t o0 = o2 & 0xFFFFu, o1 = o2 >> 16;
+                    const uint32_t o0 = o & 0xFFFFu, o1 = o >> 16;
                     *reinterpret_cast<uint32_t*>(hi + o0) = h0;
                     *reinterpret_cast<uint32_t*>(lo + o0) = l0;
                     *reinterpret_cast<uint32_t*>(hi + o1) = h1;
                     *reinterpret_cast<uint32_t*>(lo + o1) = l1;
                 }
             };
+            auto entry = [&](int f) {
+                return VEC == 4 ? static_cast<uint32_t>(reinterpret_cast<const uint16_t*>(tab)[f]) : reinterpret_cast<const uint32_t*>(tab)[f];
+            };
             if (tile != a.tail_tile) {
-                const uint32_t s = it % S::NSTG;
-                STACK_WAIT(stg_full + s, (it / S::NSTG) & 1u);
                 const float4* src = reinterpret_cast<const float4*>(stg + s * S::STG_STRIDE);
-#pragma unroll 4
-                for (int f = tid; f < a.tile_vec; f += 128) emit(f, src[f]);
+                // CB vectors (and their table entries) are loaded before the first store: the stores go to shared memory
+                // too, so the compiler cannot hoist a later iteration's loads above them by itself
+                // (full rounds run without predicates in one basic block, so that the compiler interleaves the three vectors)
+                constexpr int CB = 3;
+                int f0 = ctid;
+                for (; f0 + (int)NCT * (CB - 1) < a.tile_vec - (a.tile_vec % (int)NCT) ; f0 += NCT * CB) {
+                    float4 v[CB];
+                    uint32_t o[CB];
+#pragma unroll
+                    for (int i = 0; i < CB; ++i) { v[i] = src[f0 + (int)NCT * i]; o[i] = entry(f0 + (int)NCT * i); }
+#pragma unroll
+                    for (int i = 0; i < CB; ++i) emit(o[i], v[i]);
+                }
+                {
+                    float4 v[CB];
+                    uint32_t o[CB];
+#pragma unroll
+                    for (int i = 0; i < CB; ++i) {
+                        const int f = f0 + (int)NCT * i;
+                        if (f < a.tile_vec) { v[i] = src[f]; o[i] = entry(f); }
+                    }
+#pragma unroll
+                    for (int i = 0; i < CB; ++i)
+                        if (f0 + (int)NCT * i < a.tile_vec) emit(o[i], v[i]);
+                }
+                TR_ADD(tr2);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(stg_free + s);
-                ++it;
             } else {                                                      // the stream's last, partial 128-byte row is not in the tensor map
                 const long long e0 = static_cast<long long>(tile) * a.tile_elems;
-                for (int f = tid; f < a.tile_vec; f += 128) {
+                for (int f = ctid; f < a.tile_vec; f += NCT) {
                     const long long e = e0 + 4ll * f;
                     float4 v;
                     v.x = e + 0 < a.total_elems ? a.x_dense[e + 0] : 0.f;
                     v.y = e + 1 < a.total_elems ? a.x_dense[e + 1] : 0.f;
                     v.z = e + 2 < a.total_elems ? a.x_dense[e + 2] : 0.f;
                     v.w = e + 3 < a.total_elems ? a.x_dense[e + 3] : 0.f;
-                    emit(f, v);
+                    emit(entry(f), v);
                 }
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bx_full + b);
+            TR_ADD(tr3);
         }
-    } else if (warp < 12) {
+        TR_FLUSH(16);
+    } else if (warp < W_E2) {
         // ================================================================ epilogue 1: D1 -> y = za + zb -> bf16 hi/lo -> A2
-        const uint32_t q = warp & 3u, s = (warp - 4u) >> 2;
+        const uint32_t q = warp & 3u, s = ((warp - W_E1) >> 2) & 1u, eg = (warp - W_E1) >> 3;
         const uint32_t lane_q = (q * 32u) << 16, lane_s = (q * 32u + s * 16u) << 16;
         const int np8 = a.Np >> 3;
-        uint32_t n = 0;
-        for (int tile = first; tile < a.num_tiles; tile += stride, ++n) {
+        tr_me = tr_on && warp == W_E1 && lane == 0;
+        auto convert16 = [&](const uint32_t (&za)[8], const uint32_t (&zb)[8], uint32_t dst_hi, uint32_t dst_lo) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                split2_packed(add2_packed(pack2(za[2 * i], za[2 * i + 1]), pack2(zb[2 * i], zb[2 * i + 1])), h[i], l[i]);
+            tmem_st_frag8(dst_hi, h);
+            tmem_st_frag8(dst_lo, l);
+        };
+        uint32_t n = eg;                                                   // this CTA's tile number
+        for (int tile = first + (int)eg * stride; tile < a.num_tiles; tile += NE1G * stride, n += NE1G) {
             const uint32_t b = n & 1u;
-            STACK_WAIT(d1_full + b, (n >> 1) & 1u);
-            if (n >= 2) STACK_WAIT(a2_free + b, ((n >> 1) - 1u) & 1u);
+            const uint32_t d1 = tmem + TM_D1 + b * d1_stride;
+            TR_START();
+            {
+                bool ok = true;
+                ok = mbar_wait(d1_full + b, (n >> 1) & 1u);
+                TR_ADD(tr0);
+                if (ok && n >= 2) ok = mbar_wait(a2_free + b, ((n >> 1) - 1u) & 1u);
+                TR_ADD(tr1);
+                if (!ok) { dead = true; break; }
+            }
             tc_fence_after_sync();
-            const uint32_t d1 = tmem + TM_D1 + b * 128;
 #pragma unroll
             for (int t = 0; t < T2; ++t) {
                 const uint32_t col0 = (2 * t + s) * a.Np;                 // this warp's map of A2 tile t
                 const uint32_t src_a = d1 + lane_q + col0, src_b = src_a + (16u << 16);
                 const uint32_t dst_hi = tmem + TM_A2 + b * 64 + t * KP + lane_s, dst_lo = dst_hi + KP / 2;
-                int c8 = 0;
-                for (; c8 + 2 <= np8; c8 += 2) {                          // 16 columns of h = 8 packed A2 columns
-                    uint32_t za[8], zb[8], h[4], l[4];
-                    tmem_ld_frag16(src_a + c8 * 8, za);
-                    tmem_ld_frag16(src_b + c8 * 8, zb);
-                    tmem_ld_wait();
+                // all the map's columns are requested before the first wait (a TMEM load takes hundreds of cycles while the
+                // tensor core and the other epilogue warps use the same memory): one round trip per map instead of one per 16 columns
+                constexpr int NG = KP / 8, NB = NG > 4 ? 4 : NG;           // 8-column groups a map can have; groups per batch
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        split2_packed(add2_packed(pack2(za[2 * i], za[2 * i + 1]), pack2(zb[2 * i], zb[2 * i + 1])), h[i], l[i]);
-                    tmem_st_frag8(dst_hi + c8 * 4, h);
-                    tmem_st_frag8(dst_lo + c8 * 4, l);
-                }
-                if (c8 < np8) {                                           // 8 more columns
-                    uint32_t za[4], zb[4], h[2], l[2];
-                    tmem_ld_frag8(src_a + c8 * 8, za);
-                    tmem_ld_frag8(src_b + c8 * 8, zb);
-                    tmem_ld_wait();
+                for (int g0 = 0; g0 < NG; g0 += NB) {
+                    uint32_t za[4 * NB], zb[4 * NB];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        split2_packed(add2_packed(pack2(za[2 * i], za[2 * i + 1]), pack2(zb[2 * i], zb[2 * i + 1])), h[i], l[i]);
-                    tmem_st_frag4(dst_hi + c8 * 4, h[0], h[1]);
-                    tmem_st_frag4(dst_lo + c8 * 4, l[0], l[1]);
+                    for (int c = 0; c < NB; c += 2) {
+                        const int c8 = g0 + c;
+                        if (c8 + 2 <= np8) {
+                            tmem_ld_frag16(src_a + c8 * 8, reinterpret_cast<uint32_t (&)[8]>(za[4 * c]));
+                            tmem_ld_frag16(src_b + c8 * 8, reinterpret_cast<uint32_t (&)[8]>(zb[4 * c]));
+                        } else if (c8 < np8) {
+                            tmem_ld_frag8(src_a + c8 * 8, reinterpret_cast<uint32_t (&)[4]>(za[4 * c]));
+                            tmem_ld_frag8(src_b + c8 * 8, reinterpret_cast<uint32_t (&)[4]>(zb[4 * c]));
+                        }
+                    }
+                    tmem_ld_wait();
+                    if (t == T2 - 1 && g0 + NB >= NG) {                   // every column of D1 this warp needs is in registers
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(d1_free + b);
+                    }
+#pragma unroll
+                    for (int c = 0; c < NB; c += 2) {
+                        const int c8 = g0 + c;
+                        if (c8 + 2 <= np8) {
+                            convert16(reinterpret_cast<const uint32_t (&)[8]>(za[4 * c]), reinterpret_cast<const uint32_t (&)[8]>(zb[4 * c]),
+                                      dst_hi + c8 * 4, dst_lo + c8 * 4);
+                        } else if (c8 < np8) {
+                            uint32_t h[2], l[2];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                split2_packed(add2_packed(pack2(za[4 * c + 2 * i], za[4 * c + 2 * i + 1]), pack2(zb[4 * c + 2 * i], zb[4 * c + 2 * i + 1])),
+                                              h[i], l[i]);
+                            tmem_st_frag4(dst_hi + c8 * 4, h[0], h[1]);
+                            tmem_st_frag4(dst_lo + c8 * 4, l[0], l[1]);
+                        }
+                    }
                 }
             }
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(d1_free + b);
-                mbar_arrive(a2_full + b);
-            }
+            if (lane == 0) mbar_arrive(a2_full + b);
+            TR_ADD(tr2);
         }
-    } else if (warp < 16) {
+        TR_FLUSH(24);
+    } else if (warp < W_PROD) {
         // ================================================================ epilogue 2: D2 -> energies
-        const uint32_t q = warp & 3u, et = tid - 12 * 32;                 // thread within the role
+        const uint32_t q = warp & 3u, et = tid - W_E2 * 32;               // thread within the role
         const uint32_t lane_q = (q * 32u) << 16;
         const uint32_t s = lane >> 4, r = lane & 15u;
         const uint32_t my_set = J == 4 ? q : J == 2 ? (q >> 1) : 0u;
         const uint32_t my_v = J == 4 ? r : J == 2 ? 16u * (q & 1u) + r : 16u * q + r;
+        const uint32_t C = static_cast<uint32_t>(a.c_count);
         uint32_t n = 0;
+        // channel of the first map of the CTA's current tile, advanced without a division (n_maps < 2^30: 32-bit arithmetic)
+        uint32_t chan0 = (static_cast<uint32_t>(first) * a.MT) % C;
+        tr_me = tr_on && warp == W_E2 && lane == 0;
         for (int tile = first; tile < a.num_tiles; tile += stride, ++n) {
-            STACK_WAIT(d2_full, n & 1u);
+            const uint32_t b2 = nb2 == 2 ? (n & 1u) : 0u, use2 = nb2 == 2 ? (n >> 1) : n;
+            TR_START();
+            {
+                bool ok = true;
+                ok = mbar_wait(d2_full + b2, use2 & 1u);
+                TR_ADD(tr0);
+                if (!ok) { dead = true; break; }
+            }
             tc_fence_after_sync();
-            float* red_w = red + (n & 1u) * 32;
+            const uint32_t d2 = tmem + TM_D2 + b2 * 64 + lane_q;
+            const uint32_t m0 = static_cast<uint32_t>(tile) * a.MT;
+            float e[T2];
+            // the lane's T2 * KP (64 or 48) coefficients in two round trips of at most 32 registers; D2 is handed back as soon
+            // as the second one has landed
+            constexpr int TOT = T2 * KP, HALF = TOT >= 32 ? 32 : TOT;
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c0 = 0; c0 < TOT; c0 += HALF) {
+                uint32_t z[HALF];
+#pragma unroll
+                for (int c = 0; c < HALF; c += 16)
+                    if (c0 + c < TOT) tmem_ld16(d2 + c0 + c, reinterpret_cast<uint32_t (&)[16]>(z[c]));
+                tmem_ld_wait();
+                if (c0 + HALF >= TOT) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d2_free + b2);
+                    TR_ADD(tr2);
+                }
+#pragma unroll
+                for (int c = 0; c < HALF; c += 16) {
+                    if (c0 + c < TOT) {
+                        const int t = (c0 + c) / KP;                        // A2 tile these 16 columns belong to (KP is a multiple of 16)
+                        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            p0 = fmaf(__uint_as_float(z[c + i]), __uint_as_float(z[c + i]), p0);
+                            p1 = fmaf(__uint_as_float(z[c + 4 + i]), __uint_as_float(z[c + 4 + i]), p1);
+                            p2 = fmaf(__uint_as_float(z[c + 8 + i]), __uint_as_float(z[c + 8 + i]), p2);
+                            p3 = fmaf(__uint_as_float(z[c + 12 + i]), __uint_as_float(z[c + 12 + i]), p3);
+                        }
+                        const float p = (p0 + p1) + (p2 + p3);
+                        if (T2 == 4) part[t] += p;
+                        else if (T2 == 2) part[t] += p;
+                        else part[0] += p;
+                        if (a.dump != nullptr) {
+                            const uint32_t m = m0 + (2 * t + s) * J + my_set;
+                            const int u0 = (c0 + c) - t * KP;
+                            if (m < (uint32_t)a.n_maps && my_v < (uint32_t)a.N)
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (u0 + i < a.N) a.dump[static_cast<long long>(m) * a.NN + (u0 + i) * a.N + my_v] = __uint_as_float(z[c + i]);
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int t = 0; t < T2; ++t) {
-                float e0 = 0.f, e1 = 0.f;
+                float v = part[t];
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                e[t] = v;                                                  // lanes of one half: the warp's share of map (2t + s, my_set)
+            }
+            TR_ADD(tr3);
+            if (a.energy_out == nullptr) {
+                // production: each warp adds its fp64 share of a map straight into the channel sum (J = 1: four shares per map).
+                // The warp's 2 * T2 shares are gathered into its first lanes so that they leave in ONE atomic instruction
+                // (lane l: A2 tile t = l / 2, row slot s = l % 2; the share sits in lane 16 s).
+                float mine = 0.f;
 #pragma unroll
-                for (int c = 0; c < KP; c += 16) {
-                    uint32_t z[16];
-                    tmem_ld16(tmem + TM_D2 + lane_q + t * KP + c, z);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        e0 = fmaf(__uint_as_float(z[i]), __uint_as_float(z[i]), e0);
-                        e1 = fmaf(__uint_as_float(z[8 + i]), __uint_as_float(z[8 + i]), e1);
-                    }
-                    if (a.dump != nullptr) {
-                        const long long m = static_cast<long long>(tile) * a.MT + (2 * t + s) * J + my_set;
-                        if (m < a.n_maps && my_v < (uint32_t)a.N)
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (c + i < a.N) a.dump[m * a.NN + (c + i) * a.N + my_v] = __uint_as_float(z[i]);
+                for (int t = 0; t < T2; ++t) {
+                    const float got = __shfl_sync(0xffffffffu, e[t], (lane & 1u) * 16u);
+                    if ((lane >> 1) == (uint32_t)t) mine = got;
+                }
+                if (lane < 2u * T2) {
+                    const uint32_t ml = lane * J + my_set;                 // map (g = 2t + s = lane, my_set) of the tile
+                    if (m0 + ml < (uint32_t)a.n_maps) {
+                        uint32_t ch = chan0 + ml;
+                        while (ch >= C) ch -= C;
+                        atomicAdd(a.accum + ch, static_cast<double>(mine));
                     }
                 }
-                float e = e0 + e1;
-                e += __shfl_xor_sync(0xffffffffu, e, 8);
-                e += __shfl_xor_sync(0xffffffffu, e, 4);
-                e += __shfl_xor_sync(0xffffffffu, e, 2);
-                e += __shfl_xor_sync(0xffffffffu, e, 1);
-                if (r == 0) red_w[q * 8 + 2 * t + s] = e;
-            }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(d2_free);
-            named_bar_sync(1, 128);
-            if (et < (uint32_t)a.MT) {
-                const uint32_t g = et / J, set = et % J;
-                float e;
-                if (J == 4) e = red_w[set * 8 + g];
-                else if (J == 2) e = red_w[(2 * set) * 8 + g] + red_w[(2 * set + 1) * 8 + g];
-                else e = (red_w[g] + red_w[8 + g]) + (red_w[16 + g] + red_w[24 + g]);
-                const long long m = static_cast<long long>(tile) * a.MT + et;
-                if (m < a.n_maps) {
-                    atomicAdd(a.accum + (m % a.c_count), static_cast<double>(e));
-                    if (a.energy_out) a.energy_out[m] = e;
+            } else {
+                // per-map energies asked for: the shares of a map are summed in a fixed order (bit-reproducible fp32 energy)
+                float* red_w = red + (n & 1u) * 32;
+                if (r == 0)
+#pragma unroll
+                    for (int t = 0; t < T2; ++t) red_w[q * 8 + 2 * t + s] = e[t];
+                named_bar_sync(1, 128);
+                if (et < (uint32_t)a.MT) {
+                    const uint32_t g = et / J, set = et % J;
+                    float en;
+                    if (J == 4) en = red_w[set * 8 + g];
+                    else if (J == 2) en = red_w[(2 * set) * 8 + g] + red_w[(2 * set + 1) * 8 + g];
+                    else en = (red_w[g] + red_w[8 + g]) + (red_w[16 + g] + red_w[24 + g]);
+                    const uint32_t m = m0 + et;
+                    if (m < (uint32_t)a.n_maps) {
+                        uint32_t ch = chan0 + et;
+                        while (ch >= C) ch -= C;
+                        atomicAdd(a.accum + ch, static_cast<double>(en));
+                        a.energy_out[m] = en;
+                    }
                 }
             }
+            chan0 += a.chan_step;
+            if (chan0 >= C) chan0 -= C;
+            TR_ADD(tr1);
         }
+        TR_FLUSH(32);
     }
-#undef STACK_WAIT
+#undef TR_START
+#undef TR_ADD
+#undef TR_FLUSH
     if (dead) {                                                           // a hand-over never came: flag it and poison the result
         atomicExch(a.status, DCTP_DEV_MMA_TIMEOUT);
         for (int c = lane; c < a.c_count; c += 32) a.accum[c] = __longlong_as_double(0x7FF8000000000000ll);
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 17) tmem_dealloc<512>(tmem);
+    if (warp == W_MMA) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace dctp

@@ -118,6 +118,9 @@ int dctp_path_for(int H, int W, long long stride_h);
  * 8/4/2-byte scatter, generic 128/64/32-bit loads) at a typical table size */
 int dctp_occupancy(int kp, int mode);
 long long dctp_launch_count(void);
+/* Name of the kernel instantiation the most recent dctp_score_accum call launched (AUTO's choice made visible: bench.py labels
+ * its per-kernel table with it instead of re-deriving the dispatch).  Static storage, valid until the next score call. */
+const char* dctp_last_kernel(void);
 int dctp_sm_count(void);
 
 #ifdef __cplusplus
