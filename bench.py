@@ -377,7 +377,7 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
             e2e_scores, _ = finish_run()
             host_scores = e2e_scores.cpu()
             if rank == 0 and npy_dir is not None:
-                write_score_files(session.split_files(host_scores.numpy()), npy_dir)
+                write_score_files(session.split_files(host_scores.numpy()), npy_dir, verbose=False)
             e1.record()
             barrier(world)
             ms_e2e = max_over_ranks(e0.elapsed_time(e1), device, world)

@@ -710,7 +710,7 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
     a.n_items = a.n_maps * a.NVC;
     a.c_hi = reinterpret_cast<const uint8_t*>(basis.hi); a.c_lo = reinterpret_cast<const uint8_t*>(basis.lo);
     a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
-    if (energy_out) CUDA_TRY(cudaMemsetAsync(energy_out, 0, sizeof(float) * a.n_maps, stream));
+    if (energy_out) CUDA_TRY(cudaMallocAsync(&a.energy_parts, sizeof(float) * a.n_maps * a.NVC, stream));   // (debug / parity output only)
     int grid = g.sm_count < a.n_items ? g.sm_count : a.n_items;
     static long long* trace_buf = nullptr;
     const bool tracing = std::getenv("DCTP_L_TRACE") != nullptr;
@@ -719,6 +719,10 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
         a.trace = trace_buf;
     }
     CUDA_TRY(launch_score(score_large_kernel, grid, LARGE_NT, LargeSmem::TOTAL, stream, a));
+    if (energy_out) {
+        sum_parts_kernel<<<(a.n_maps + 255) / 256, 256, 0, stream>>>(a.energy_parts, a.NVC, energy_out, a.n_maps);
+        CUDA_TRY(cudaFreeAsync(a.energy_parts, stream));
+    }
     note_kernel("score_large_kernel (tcgen05, tiled two-stage, 18 warps)");
     if (tracing) {
         long long h[16];

@@ -44,7 +44,9 @@ struct LargeScoreArgs {
     const uint8_t* c_hi;            // basis image, bf16: [column blocks of 64][NPR rows][128 B], 16-B chunks XOR-swizzled by
     const uint8_t* c_lo;            //   (row & 7): any (8-aligned row range, column block) is one contiguous operand slab
     double* accum;
-    float* energy_out;              // optional [n_maps], accumulated with float atomics over the v-chunks (caller zeroes)
+    float* energy_out;              // (unused by the kernel: the host sums energy_parts into it)
+    float* energy_parts;            // optional [n_maps][NVC]: each work item's share of its map's energy; summed in a fixed order by
+                                    // sum_parts_kernel, so per-map energies are bit-reproducible like the other kernels'
     float* dump;                    // optional [n_maps][N][N] coefficients Z[u][v]
     int* status;
     long long* trace;               // bring-up aid: cycles the control thread of CTA 0 spent in each kind of wait
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (tid == 0) {
                     atomicAdd(a.accum + (map % a.c_count), (double)s);
-                    if (a.energy_out) atomicAdd(a.energy_out + map, s);
+                    if (a.energy_parts) a.energy_parts[(size_t)map * a.NVC + vc] = s;
                 }
             }
             named_bar_sync(1, NC);
@@ -451,6 +453,16 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// energy_out[m] = parts[m][0] + parts[m][1] + ... (fixed order)
+__global__ void sum_parts_kernel(const float* parts, int nvc, float* out, int n) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n) {
+        float s = 0.f;
+        for (int j = 0; j < nvc; ++j) s += parts[(size_t)m * nvc + j];
+        out[m] = s;
+    }
 }
 
 }  // namespace dctp

@@ -121,11 +121,9 @@ def inference(net, loader, limit, device, rank=0, world=1):
     return n
 
 
-def imp_score(net, args, loader=None, out_root='importance_score', write=True, path='auto'):
-    """Score every hook site of `net` over `args.limit` batches and write the reference's files.
-
-    args: namespace with .net, .limit, .batch_size (and optionally .seed_base).  Returns
-    {file_stem: float32 vector}.  The net must already live on a CUDA device."""
+def score_session(net, args, loader=None, path='auto'):
+    """Run the scoring pass (all hook sites live, `args.limit` batches, this rank's shard of every batch) and return the
+    ScoreSession with its per-site energy sums still on the device, not yet reduced or finalised."""
     import torch.distributed as dist
     device = next(net.parameters()).device
     if device.type != 'cuda':
@@ -144,7 +142,19 @@ def imp_score(net, args, loader=None, out_root='importance_score', write=True, p
         session.plan_layout(torch.zeros(1, 3, side0, side0, device=device))
     with session:
         inference(net, loader, args.limit, device, rank=rank, world=world)
+    return session
+
+
+def imp_score(net, args, loader=None, out_root='importance_score', write=True, path='auto'):
+    """Score every hook site of `net` over `args.limit` batches and write the reference's files.
+
+    args: namespace with .net, .limit, .batch_size (and optionally .seed_base).  Returns
+    {file_stem: float32 vector}.  The net must already live on a CUDA device."""
+    import torch.distributed as dist
+    session = score_session(net, args, loader=loader, path=path)
     files = session.finalize()
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
     if write and rank == 0:
         write_score_files(files, score_dir(args.net, args.limit, out_root))
     if world > 1:
@@ -152,9 +162,10 @@ def imp_score(net, args, loader=None, out_root='importance_score', write=True, p
     return files
 
 
-def write_score_files(files, directory):
+def write_score_files(files, directory, verbose=True):
     os.makedirs(directory, exist_ok=True)
     for stem, vec in files.items():
         np.save(os.path.join(directory, stem + '.npy'), np.ascontiguousarray(vec, dtype=np.float32))
-        print(os.path.join(directory, stem) + ':done!')       # common.py:395
+        if verbose:
+            print(os.path.join(directory, stem) + ':done!')   # common.py:395
     return directory

@@ -38,12 +38,18 @@ class ScoreSession:
         self.lib = _lib.load()
         self._score_accum = self.lib.dctp_score_accum
         self._plans = [None] * len(self.sites)
+        self._planned = False                 # plan_layout() ran: slots exist for every site, in site order
         self.launches = 0
 
     # ------------------------------------------------------------------ registration
     def register(self):
         if self.handles:
             raise RuntimeError('hooks already registered')
+        from .dist import world_size
+        if world_size() > 1 and not self._planned:
+            # every rank runs this same line, so all of them fail here, before any forward pass and before the collective
+            raise RuntimeError('multi-rank run: call plan_layout(example) before registering the hooks, so that every rank holds the '
+                               'same accumulator layout even if its shard of the batches is empty (generate.score_session does)')
         for idx, site in enumerate(self.sites):
             module = resolve_module(self.net, site.module)
             self.handles.append(module.register_forward_hook(self._make_hook(idx, site)))
@@ -150,6 +156,7 @@ class ScoreSession:
             C = shape[1]
             c_count = DENSENET_WINDOW if site.variant == VARIANT_LAST12 else C
             self._slot(idx, c_count, example.device)
+        self._planned = True
         return self
 
     # ------------------------------------------------------------------ CUDA-graph replay (launch-bound nets)

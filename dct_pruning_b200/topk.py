@@ -45,6 +45,32 @@ def select_index(imp, k, device='cuda'):
     return topk_segmented(t, [0, t.numel()], [k])[0].cpu().numpy()
 
 
+def kept_channels_device(net_name, compress_rate, device_scores, segments, origin_rates=None):
+    """Same selections as `kept_channels`, from the flat score vector still on the device (ScoreSession.finalize_device) and its
+    [(file stem, offset, length)] segments (ScoreSession.file_segments): the scores go from the finalise kernel to the top-k
+    kernel without a host round trip.  Returns [(Selection, int64 numpy array)]."""
+    rates = get_compress_rate(compress_rate) if isinstance(compress_rate, str) else list(compress_rate)
+    plan = selection_plan(net_name, rates, origin_rates)
+    if not plan:
+        return []
+    where = {stem: (off, n) for stem, off, n in segments}
+    pieces, offsets, ks = [], [0], []
+    for sel in plan:
+        off, n = where[sel.stem]
+        if n != sel.C:
+            raise ValueError('%s: score vector has %d entries, layer has %d channels' % (sel.stem, n, sel.C))
+        pieces.append(device_scores[off:off + n])
+        offsets.append(offsets[-1] + n)
+        ks.append(sel.k)
+    kept = topk_segmented(torch.cat(pieces), offsets, ks)
+    host = torch.cat(kept).cpu().numpy() if kept else np.zeros(0, np.int64)
+    out, at = [], 0
+    for sel in plan:
+        out.append((sel, host[at:at + sel.k].copy()))
+        at += sel.k
+    return out
+
+
 def kept_channels(net_name, compress_rate, scores, device='cuda', origin_rates=None):
     """For every selection the reference's loader for `net_name` performs under `compress_rate`
     (string or list of floats), the kept channel ids.  `scores` maps file stem -> vector (numpy or

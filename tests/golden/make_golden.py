@@ -185,6 +185,11 @@ SCORE_CASES = [  # tag, net, batch, side, limit
     ('resnet_50_s224_b1_l1', 'resnet_50', 1, 224, 1),
     ('u2netp_s64_b1_l2', 'u2netp', 1, 64, 2),
     ('u2netp_s144_b1_l1', 'u2netp', 1, 144, 1),
+    # the headline sizes themselves (round 2): BASELINE config 5's 320x320, the 288x288 the reference's DUTS loader really
+    # feeds (utils/common.py:154-155), and ResNet-50@224 with more than one image
+    ('u2netp_s288_b1_l1', 'u2netp', 1, 288, 1),
+    ('u2netp_s320_b1_l1', 'u2netp', 1, 320, 1),
+    ('resnet_50_s224_b2_l1', 'resnet_50', 2, 224, 1),
 ]
 
 

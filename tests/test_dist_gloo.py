@@ -61,3 +61,53 @@ def test_rank_slice_partitions_every_batch():
             parts = [rank_slice(n, r, world) for r in range(world)]
             assert parts[0][0] == 0 and parts[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+
+
+def session_worker(rank, world, port_no, out_dir, give_layout_to_all):
+    """ScoreSession's end-of-run collective with an EMPTY shard on rank 1 (batch size smaller than the world size):
+    the rank whose hooks never fired must still enter the all-reduce - with zeros and count 0 - instead of raising before it."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port_no), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from dct_pruning_b200 import dist as ddist
+    from dct_pruning_b200.hooks import ScoreSession
+    from dct_pruning_b200.zoo import get_network
+    ddist.init_from_env(backend='gloo')
+    torch.manual_seed(0)
+    net = get_network('resnet_56').eval()
+    session = ScoreSession(net, 'resnet_56')
+    if give_layout_to_all:
+        session.plan_layout(torch.zeros(1, 3, 32, 32))           # shape-only forward: slots for all 55 sites, in site order
+        assert session.used == 2032 and all(s is not None for s in session.slots)
+    if rank == 0 and give_layout_to_all:                         # this rank "scored" 3 images (the kernels themselves need a GPU)
+        session.flat[:session.used] = torch.arange(session.used, dtype=torch.float64) + 1.0
+        session.images = [3] * len(session.sites)
+    result = 'ok'
+    try:
+        session.register()                                       # (refuses a multi-rank run without a planned layout)
+        session.remove()
+        n_images = session.reduce_sums()
+        np.save(os.path.join(out_dir, 'flat%d.npy' % rank), session.flat[:session.used + 1].numpy())
+        assert n_images == 3.0
+    except RuntimeError as e:
+        result = 'raised: %s' % e
+    with open(os.path.join(out_dir, 'result%d.txt' % rank), 'w') as f:
+        f.write(result)
+    dist.barrier()                                               # nobody is left behind in a collective
+    ddist.shutdown()
+
+
+def test_empty_shard_enters_the_all_reduce(tmp_path):
+    mp.spawn(session_worker, args=(2, free_port(), str(tmp_path), True), nprocs=2, join=True)
+    assert [open(os.path.join(str(tmp_path), 'result%d.txt' % r)).read() for r in range(2)] == ['ok', 'ok']
+    a, b = (np.load(os.path.join(str(tmp_path), 'flat%d.npy' % r)) for r in range(2))
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(a[:-1], np.arange(2032) + 1.0)
+    assert a[-1] == 3.0
+
+
+def test_multi_rank_run_without_a_planned_layout_fails_on_every_rank_up_front(tmp_path):
+    """Without plan_layout a rank with an empty shard would hold no accumulator and could not enter the all-reduce (the others
+    would wait in it forever): the session refuses to register its hooks on every rank, before any forward pass."""
+    mp.spawn(session_worker, args=(2, free_port(), str(tmp_path), False), nprocs=2, join=True)
+    res = [open(os.path.join(str(tmp_path), 'result%d.txt' % r)).read() for r in range(2)]
+    assert all(r.startswith('raised') and 'plan_layout' in r for r in res), res

@@ -18,7 +18,9 @@ from conftest import golden_scores
 pytestmark = pytest.mark.gpu
 
 CASES = ['vgg_16_bn_b3_l2', 'resnet_56_b2_l2', 'resnet_110_b1_l1', 'densenet_40_b2_l1', 'googlenet_b2_l1',
-         'resnet_50_s64_b2_l1', 'resnet_50_s224_b1_l1', 'u2netp_s64_b1_l2', 'u2netp_s144_b1_l1']
+         'resnet_50_s64_b2_l1', 'resnet_50_s224_b1_l1', 'u2netp_s64_b1_l2', 'u2netp_s144_b1_l1',
+         # the headline sizes themselves (BASELINE configs 4 and 5; 288 is what the reference's DUTS loader feeds)
+         'resnet_50_s224_b2_l1', 'u2netp_s288_b1_l1', 'u2netp_s320_b1_l1']
 
 
 def generate(tag, device, path='auto'):
@@ -64,7 +66,10 @@ def test_scores_match_reference_end_to_end(lib, cuda_device, tag):
 
 
 STRICT = [('vgg_16_bn', 3, 32, 2), ('resnet_56', 2, 32, 1), ('densenet_40', 2, 32, 1), ('googlenet', 2, 32, 1),
-          ('resnet_50', 1, 64, 1), ('u2netp', 1, 32, 1)]
+          ('resnet_50', 1, 64, 1), ('u2netp', 1, 32, 1),
+          # large maps inside a net: 160 / 320 reach the tiled large-map kernel, 80 the 128-wide smem-operand kernel,
+          # 40 / 20 / 10 the stacked-basis kernel, 5 the Kronecker kernel; ResNet-50 at its real input size
+          ('u2netp', 1, 160, 1), ('u2netp', 1, 320, 1), ('resnet_50', 1, 224, 1)]
 
 
 @pytest.mark.parametrize('net_name,batch,side,limit', STRICT)
