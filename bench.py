@@ -231,6 +231,7 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
     def one_step():
         for i in live:
             session.score(i, acts[i])
+        session.flush()                                             # (sites held for a multi-site launch)
 
     # ---- warm-up (bases uploaded, slots allocated, clocks up), then the kernel the library picked for every site
     for _ in range(max(args.warmup, 3)):
@@ -239,14 +240,16 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
     _lib.check(lib.dctp_check(None))
     session.reset()
     site_kernel = {}
+    defer_bytes, session.defer_bytes = session.defer_bytes, 0      # one launch per site while asking which kernel it runs
     for i in live:
         session.score(i, acts[i])
         site_kernel[i] = lib.dctp_last_kernel().decode()
     torch.cuda.synchronize()
+    session.defer_bytes = defer_bytes
     session.reset()
 
     # ---- the timed region: K steps of back-to-back hook launches + the end-of-run kernels, nothing else on the stream
-    step_graph = None
+    step_graph, graph_launches = None, 0
     if args.graph and live:
         warm_stream = torch.cuda.Stream(device=device)
         warm_stream.wait_stream(torch.cuda.current_stream())
@@ -255,8 +258,11 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
         torch.cuda.current_stream().wait_stream(warm_stream)
         torch.cuda.synchronize()
         step_graph = torch.cuda.CUDAGraph()
+        g0 = lib.dctp_launch_count()
         with torch.cuda.graph(step_graph):
             one_step()
+            session.flush()
+        graph_launches = lib.dctp_launch_count() - g0
         session.reset()
     barrier(world)
     launches0 = lib.dctp_launch_count()
@@ -272,7 +278,7 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
     finish_run()
     t1.record()
     barrier(world)
-    launches = lib.dctp_launch_count() - launches0 + (steps * len(live) if step_graph is not None else 0)
+    launches = lib.dctp_launch_count() - launches0 + (steps * graph_launches if step_graph is not None else 0)
     _lib.check(lib.dctp_check(None))
     ms_total = max_over_ranks(t0.elapsed_time(t1), device, world)
     out.update(ms_per_step=ms_total / steps, gpu_launches=int(launches), hook_sites=len(session.sites),
@@ -283,6 +289,7 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
     # ---- per-launch durations: the same K steps again with an event pair around every launch (isolated launch durations:
     #      the events keep consecutive launches from overlapping; not part of the timed value)
     session.reset()
+    session.defer_bytes = 0                                         # (isolated launches: no multi-site batching in this pass)
     ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in live] for _ in range(steps)]
     for step in range(steps):
         for j, i in enumerate(live):
@@ -290,6 +297,7 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
             session.score(i, acts[i])
             ev[step][j][1].record()
     torch.cuda.synchronize()
+    session.defer_bytes = defer_bytes
     session.reset()
     per_site_ms = {i: statistics.mean(ev[s][j][0].elapsed_time(ev[s][j][1]) for s in range(steps)) for j, i in enumerate(live)}
 
@@ -517,6 +525,7 @@ def run_ours(args):
                        'parallelism': 'batch-sharded x%d, 1 all-reduce per run' % world,
                        'peaks': {'hbm_gbs': hbm_peak, 'bf16_tflops_sustained': tflops, 'kind': peak_kind}},
             'gpu_launches': main['gpu_launches'],
+            'launch_batching': 'activations below %d MB are held and scored up to 16 sites per launch (dctp_score_accum_multi)' % (64),
             'roofline': main.get('roofline'),
             'hook_path_GBps': main['hook_path_GBps'],
             'binding_roofline_frac': main['binding_roofline_frac'],

@@ -25,6 +25,7 @@ _SIGNATURES = {
                                     _c.c_int, _c.c_int,
                                     _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                     _c.c_int, _c.c_void_p]),
+    'dctp_score_accum_multi': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     'dctp_finalize': (_c.c_int, [_c.c_void_p, _c.c_double, _c.c_void_p, _c.c_int, _c.c_void_p]),
     'dctp_topk_segmented': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                        _c.c_void_p, _c.c_void_p, _c.c_void_p]),
@@ -40,6 +41,11 @@ _SIGNATURES = {
     'dctp_sm_count': (_c.c_int, []),
 }
 EXPORTS = tuple(_SIGNATURES)
+
+
+class Site(_c.Structure):
+    """dctp_site of include/dctp.h: one dense activation of a multi-site launch."""
+    _fields_ = [('x', _c.c_void_p), ('accum', _c.c_void_p), ('B', _c.c_int), ('c_count', _c.c_int)]
 
 
 class DctpError(RuntimeError):

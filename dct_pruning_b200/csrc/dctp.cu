@@ -302,7 +302,7 @@ int get_stack_basis(int N, StackBasis& out) {
 //   cfg 1: the same with two epilogue-1 groups, 31 warps            cfg 2: 4 converter warps in one group, 19 warps
 // measured on B200, [256,C,N,N] 56x56 / 28x28 / 14x14, TB/s: cfg 0 3.85 / 3.67 / 3.26, cfg 1 3.78 / 3.57 / 3.12, cfg 2 3.59 / 3.31 / 2.89
 constexpr int STACK_CFGS = 3;
-typedef void (*StackKernel)(const CUtensorMap, const StackArgs);
+typedef void (*StackKernel)(const ScoreTensorMaps, const StackArgs);
 template <int NCONV, int NE1G, int NCG>
 StackKernel stack_kernel_of(int v) {
     switch (v) {
@@ -328,42 +328,65 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 template <typename Args>
-cudaError_t launch_score_tma(void (*kern)(const CUtensorMap, const Args), int grid, int block, size_t smem, cudaStream_t stream,
-                             const CUtensorMap& map, const Args& args);
+cudaError_t launch_score_tma(void (*kern)(const ScoreTensorMaps, const Args), int grid, int block, size_t smem, cudaStream_t stream,
+                             const ScoreTensorMaps& maps, const Args& args);
 
-int launch_stack(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
+struct SiteDesc { const float* first; int B; int c_count; double* accum; };     // one dense activation: B * c_count maps back to back
+
+// 2-D tensor map over a dense fp32 stream viewed as [rows, 32 floats] (whole 128-byte rows only), box = `box_rows` rows
+int encode_flat_map(CUtensorMap& map, const float* first, long long total_elems, int box_rows) {
+    std::memset(&map, 0, sizeof map);
+    const long long rows = total_elems / 32;
+    if (rows <= 0) return DCTP_OK;                           // (never dereferenced: the only tile is converted from global memory)
+    cuuint64_t gdim[2] = {32, static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {128};
+    cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)}, estr[2] = {1, 1};
+    const CUresult r = reinterpret_cast<EncodeTiledFn>(g.encode_tiled)(
+        &map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(first), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DCTP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %lld rows, box %d", (int)r, rows, box_rows);
+    return DCTP_OK;
+}
+
+// fills seg (tile ranges, per-site sizes); returns the launch's tile count
+int fill_segments(ScoreSegments& seg, const SiteDesc* sites, int n, int NN, int maps_per_tile) {
+    seg.n_seg = n;
+    int tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        seg.tile0[i] = tiles;
+        seg.n_maps[i] = sites[i].B * sites[i].c_count;
+        seg.c_count[i] = sites[i].c_count;
+        seg.total_elems[i] = static_cast<long long>(seg.n_maps[i]) * NN;
+        seg.x[i] = sites[i].first;
+        seg.accum[i] = sites[i].accum;
+        tiles += (seg.n_maps[i] + maps_per_tile - 1) / maps_per_tile;
+    }
+    for (int i = n; i <= SCORE_MAX_SEG; ++i) seg.tile0[i] = tiles;
+    return tiles;
+}
+
+// up to SCORE_MAX_SEG dense activations of side N in ONE launch (energy_out / coeff_out: single-site launches only)
+int launch_stack(const SiteDesc* sites, int n, int N, float* energy_out, float* coeff_out, cudaStream_t stream) {
     StackBasis basis;
     int rc = get_stack_basis(N, basis);
     if (rc) return rc;
     StackArgs a;
     std::memset(&a, 0, sizeof a);
     const int KP = basis.kp, J = stack_sets(KP);
-    a.x_dense = first; a.n_maps = B * c_count; a.c_count = c_count;
     a.N = N; a.NN = N * N; a.Np = (N + 7) / 8 * 8; a.G = stack_g(KP); a.MT = a.G * J;
-    a.total_elems = static_cast<long long>(a.n_maps) * a.NN;
     a.ncols = a.G * a.Np;
     a.tile_elems = a.MT * a.NN; a.tile_rows = a.tile_elems / 32; a.tile_vec = basis.tile_vec;
-    a.num_tiles = (a.n_maps + a.MT - 1) / a.MT;
-    a.tail_tile = (a.total_elems % 32) != 0 ? a.num_tiles - 1 : -1;
+    a.num_tiles = fill_segments(a.seg, sites, n, a.NN, a.MT);
     a.idesc1 = umma::make_idesc_bf16(128, a.ncols, false, false);
     a.idesc2 = umma::make_idesc_bf16(128, KP, false, false);
     a.lbo1 = basis.lbo1;
     a.a_img = basis.a_img; a.c2_hi = basis.c2_hi; a.c2_lo = basis.c2_lo; a.table = basis.table; a.table_bytes = basis.table_bytes;
-    a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
-    CUtensorMap map;
-    std::memset(&map, 0, sizeof map);
-    const long long rows = a.total_elems / 32;
-    if (rows > 0) {
-        cuuint64_t gdim[2] = {32, static_cast<cuuint64_t>(rows)};
-        cuuint64_t gstr[1] = {128};
-        cuuint32_t box[2] = {32, static_cast<cuuint32_t>(a.tile_rows)}, estr[2] = {1, 1};
-        const CUresult r = reinterpret_cast<EncodeTiledFn>(g.encode_tiled)(
-            &map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(first), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(DCTP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %lld rows, box %d", (int)r, rows, a.tile_rows);
-    }
+    a.energy_out = n == 1 ? energy_out : nullptr; a.dump = n == 1 ? coeff_out : nullptr; a.status = g.status;
+    ScoreTensorMaps maps;
+    for (int i = 0; i < n; ++i)
+        if ((rc = encode_flat_map(maps.m[i], sites[i].first, a.seg.total_elems[i], a.tile_rows))) return rc;
+    for (int i = n; i < SCORE_MAX_SEG; ++i) maps.m[i] = maps.m[0];
     int grid = g.sm_count < a.num_tiles ? g.sm_count : a.num_tiles;
-    a.chan_step = static_cast<int>((static_cast<long long>(grid) * a.MT) % c_count);
     const size_t smem = StackSmem::TOTAL;
     const bool v4 = basis.vec == 4;
     static long long* trace_buf = nullptr;
@@ -374,20 +397,20 @@ int launch_stack(const float* first, int B, int N, int c_count, double* accum, f
         a.trace = trace_buf;
     }
     const int variant = KP == 16 ? (v4 ? 0 : 1) : KP == 32 ? (v4 ? 2 : 3) : KP == 48 ? 4 : 5;
-    CUDA_TRY(launch_score_tma(stack_kernel_fn(g.stack_cfg, variant), grid, stack_threads(g.stack_cfg), smem, stream, map, a));
+    CUDA_TRY(launch_score_tma(stack_kernel_fn(g.stack_cfg, variant), grid, stack_threads(g.stack_cfg), smem, stream, maps, a));
     note_kernel("score_stack_kernel<KP=%d,VEC=%d,cfg%d> (tcgen05, stacked hi/lo basis in TMEM, TMA tile ring, warp specialised)", KP, basis.vec, g.stack_cfg);
     if (tracing) {
         long long h[64];
         CUDA_TRY(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
-        const double n = h[14] > 0 ? double(h[14]) : 1.0;
+        const double nt = h[14] > 0 ? double(h[14]) : 1.0;
         fprintf(stderr, "[dctp trace] stack N=%d cfg %d, CTA 0, %lld tiles, cycles per tile | producer: wait slot %.0f | converter: wait Bx free %.0f, "
                         "wait TMA %.0f, convert %.0f, fence+arrive %.0f | issuer 1: wait Bx %.0f, wait D1 free %.0f, issue %.0f | issuer 2: wait A2 %.0f, "
                         "wait D2 free %.0f, issue %.0f | epi1 (first group, per tile of the CTA): wait D1 %.0f, wait A2 free %.0f, work %.0f | "
                         "epi2: wait D2 %.0f, TMEM loads %.0f, sums+shuffles %.0f, atomics %.0f\n",
-                N, g.stack_cfg, h[14], h[0] / n, h[16] / n, h[17] / n, h[18] / n, h[19] / n, h[8] / n, h[9] / n, h[10] / n, h[40] / n, h[41] / n,
-                h[42] / n, h[24] / n, h[25] / n, h[26] / n, h[32] / n, h[34] / n, h[35] / n, h[33] / n);
+                N, g.stack_cfg, h[14], h[0] / nt, h[16] / nt, h[17] / nt, h[18] / nt, h[19] / nt, h[8] / nt, h[9] / nt, h[10] / nt, h[40] / nt,
+                h[41] / nt, h[42] / nt, h[24] / nt, h[25] / nt, h[26] / nt, h[32] / nt, h[34] / nt, h[35] / nt, h[33] / nt);
     }
-    ++g.launches;
+    g.launches += 1;
     CUDA_TRY(cudaGetLastError());
     return DCTP_OK;
 }
@@ -419,7 +442,7 @@ int get_kron_basis(int N, KronBasis& out) {
     return DCTP_OK;
 }
 
-int launch_kron(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
+int launch_kron(const SiteDesc* sites, int n, int N, float* energy_out, float* coeff_out, cudaStream_t stream) {
     KronBasis basis;
     int rc = get_kron_basis(N, basis);
     if (rc) return rc;
@@ -427,51 +450,45 @@ int launch_kron(const float* first, int B, int N, int c_count, double* accum, fl
     std::memset(&a, 0, sizeof a);
     const int NN = N * N, K2 = (NN + 15) / 16 * 16;
     const bool even = (N % 2) == 0;
-    a.x_dense = first; a.n_maps = B * c_count; a.c_count = c_count; a.N = N; a.NN = NN;
-    a.total_elems = static_cast<long long>(a.n_maps) * NN;
+    a.N = N; a.NN = NN;
     a.idesc = umma::make_idesc_bf16(128, K2, false, false);
     a.k_hi = basis.hi; a.k_lo = basis.lo;
-    a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
-    a.tail_tile = -1;
-    CUtensorMap map;
-    std::memset(&map, 0, sizeof map);
-    CUresult r = CUDA_SUCCESS;
+    a.energy_out = n == 1 ? energy_out : nullptr; a.dump = n == 1 ? coeff_out : nullptr; a.status = g.status;
     if (even) {
         a.sub_tiles = N == 8 ? 1 : 2;
         a.row_floats = NN + (((NN / 4) % 2) == 0 ? 4 : 0);            // an odd number of 16-byte units per row: conflict-free 128-bit reads
         a.tile_maps = 128 * a.sub_tiles;
         a.box_rows = a.tile_maps;
         a.tile_bytes = static_cast<uint32_t>(a.tile_maps) * a.row_floats * 4u;
-        cuuint64_t gdim[2] = {static_cast<cuuint64_t>(NN), static_cast<cuuint64_t>(a.n_maps)};
-        cuuint64_t gstr[1] = {static_cast<cuuint64_t>(NN) * 4};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(a.row_floats), static_cast<cuuint32_t>(a.tile_maps)}, estr[2] = {1, 1};
-        r = reinterpret_cast<EncodeTiledFn>(g.encode_tiled)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(first), gdim, gstr, box, estr,
-                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         a.sub_tiles = N == 7 ? 1 : N == 5 ? 2 : 4;
         a.row_floats = NN;
         a.tile_maps = 128 * a.sub_tiles;
         a.box_rows = a.tile_maps * NN / 32;
         a.tile_bytes = static_cast<uint32_t>(a.box_rows) * 128u;
-        const long long rows = a.total_elems / 32;
-        if (rows > 0) {
-            cuuint64_t gdim[2] = {32, static_cast<cuuint64_t>(rows)};
-            cuuint64_t gstr[1] = {128};
-            cuuint32_t box[2] = {32, static_cast<cuuint32_t>(a.box_rows)}, estr[2] = {1, 1};
-            r = reinterpret_cast<EncodeTiledFn>(g.encode_tiled)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(first), gdim, gstr, box,
-                                                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    a.num_tiles = fill_segments(a.seg, sites, n, NN, a.tile_maps);
+    ScoreTensorMaps maps;
+    for (int i = 0; i < n; ++i) {
+        if (even) {
+            std::memset(&maps.m[i], 0, sizeof(CUtensorMap));
+            cuuint64_t gdim[2] = {static_cast<cuuint64_t>(NN), static_cast<cuuint64_t>(a.seg.n_maps[i])};
+            cuuint64_t gstr[1] = {static_cast<cuuint64_t>(NN) * 4};
+            cuuint32_t box[2] = {static_cast<cuuint32_t>(a.row_floats), static_cast<cuuint32_t>(a.tile_maps)}, estr[2] = {1, 1};
+            const CUresult r = reinterpret_cast<EncodeTiledFn>(g.encode_tiled)(
+                &maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sites[i].first), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(DCTP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d maps of side %d", (int)r, a.seg.n_maps[i], N);
+        } else if ((rc = encode_flat_map(maps.m[i], sites[i].first, a.seg.total_elems[i], a.box_rows))) {
+            return rc;
         }
     }
-    if (r != CUDA_SUCCESS) return fail(DCTP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d maps of side %d", (int)r, a.n_maps, N);
-    a.num_tiles = (a.n_maps + a.tile_maps - 1) / a.tile_maps;
-    if (!even && (a.total_elems % 32) != 0) a.tail_tile = a.num_tiles - 1;
+    for (int i = n; i < SCORE_MAX_SEG; ++i) maps.m[i] = maps.m[0];
     const int grid = g.sm_count < a.num_tiles ? g.sm_count : a.num_tiles;
     const size_t smem = KronSmem::TOTAL;
 #define KRON_LAUNCH(K2V)                                                                                                         \
-    CUDA_TRY(even ? launch_score_tma(score_kron_kernel<K2V, true>, grid, KRON_NT, smem, stream, map, a)                         \
-                  : launch_score_tma(score_kron_kernel<K2V, false>, grid, KRON_NT, smem, stream, map, a))
+    CUDA_TRY(even ? launch_score_tma(score_kron_kernel<K2V, true>, grid, KRON_NT, smem, stream, maps, a)                        \
+                  : launch_score_tma(score_kron_kernel<K2V, false>, grid, KRON_NT, smem, stream, maps, a))
     switch (K2) {
         case 16: KRON_LAUNCH(16); break;
         case 32: KRON_LAUNCH(32); break;
@@ -480,7 +497,7 @@ int launch_kron(const float* first, int B, int N, int c_count, double* accum, fl
     }
 #undef KRON_LAUNCH
     note_kernel("score_kron_kernel<K2=%d,%s> (tcgen05, single-stage Kronecker, TMA tile ring, warp specialised)", K2, even ? "even" : "odd");
-    ++g.launches;
+    g.launches += 1;
     CUDA_TRY(cudaGetLastError());
     return DCTP_OK;
 }
@@ -549,8 +566,8 @@ cudaError_t launch_score(void (*kern)(const Args), int grid, int block, size_t s
 }
 
 template <typename Args>
-cudaError_t launch_score_tma(void (*kern)(const CUtensorMap, const Args), int grid, int block, size_t smem, cudaStream_t stream,
-                             const CUtensorMap& map, const Args& args) {
+cudaError_t launch_score_tma(void (*kern)(const ScoreTensorMaps, const Args), int grid, int block, size_t smem, cudaStream_t stream,
+                             const ScoreTensorMaps& map, const Args& args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(static_cast<unsigned>(block));
@@ -866,10 +883,16 @@ int launch_umma(const float* x, int B, int N, long long stride_b, long long stri
     const float* first = x + static_cast<long long>(c_begin) * stride_c;
     const bool dense = basis.scatter != nullptr && stride_c == a.NN && (B == 1 || stride_b == static_cast<long long>(c_count) * a.NN) &&
                        (reinterpret_cast<uintptr_t>(first) % 16) == 0;
-    if (KP == 64 && allow_t && dense && g.kron_on && N <= 8) return launch_kron(first, B, N, c_count, accum, energy_out, coeff_out, stream);
+    if (KP == 64 && allow_t && dense && g.kron_on && N <= 8) {
+        const SiteDesc one = {first, B, c_count, accum};
+        return launch_kron(&one, 1, N, energy_out, coeff_out, stream);
+    }
     if (KP == 64 && allow_t && dense && g.stack_on && stack_shape_supported(N) &&
         static_cast<long long>(a.n_maps) * a.NN * 4 >= g.stack_min_bytes)
-        return launch_stack(first, B, N, c_count, accum, energy_out, coeff_out, stream);
+    {
+        const SiteDesc one = {first, B, c_count, accum};
+        return launch_stack(&one, 1, N, energy_out, coeff_out, stream);
+    }
     if (KP == 64 && allow_t && dense && t_stream_ok(N, a.n_maps) && t_launch_ok(N, static_cast<long long>(a.n_maps) * a.NN * 4))
         return launch_t(first, B, N, c_count, accum, energy_out, coeff_out, stream);
     int mode;
@@ -1077,7 +1100,8 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
                                (B == 1 || stride_b == static_cast<long long>(c_count) * H * W) && (reinterpret_cast<uintptr_t>(first) % 16) == 0;
             if (H != W || H > 8 || !dense)
                 return fail(DCTP_E_UNSUPPORTED, "Kronecker path takes dense 16-B aligned square maps of side <= 8 (got %dx%d)", H, W);
-            return launch_kron(first, B, H, c_count, accum, energy_out, coeff_out, s);
+            const SiteDesc one = {first, B, c_count, accum};
+            return launch_kron(&one, 1, H, energy_out, coeff_out, s);
         }
         case DCTP_PATH_STACK: {
             const float* first = x + static_cast<long long>(c_begin) * stride_c;
@@ -1085,7 +1109,8 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
                                (B == 1 || stride_b == static_cast<long long>(c_count) * H * W) && (reinterpret_cast<uintptr_t>(first) % 16) == 0;
             if (H != W || !stack_shape_supported(H) || !dense)
                 return fail(DCTP_E_UNSUPPORTED, "stacked-basis path takes dense 16-B aligned square maps of even side 10..64 (above 32: multiples of 4) (got %dx%d)", H, W);
-            return launch_stack(first, B, H, c_count, accum, energy_out, coeff_out, s);
+            const SiteDesc one = {first, B, c_count, accum};
+            return launch_stack(&one, 1, H, energy_out, coeff_out, s);
         }
         case DCTP_PATH_LARGE: {
             const float* first = x + static_cast<long long>(c_begin) * stride_c;
@@ -1105,6 +1130,43 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
         default:
             return fail(DCTP_E_INVALID, "unknown path %d", path);
     }
+}
+
+int dctp_score_accum_multi(const dctp_site* sites, int n_sites, int H, int W, void* stream) {
+    std::vector<int> single;                                 // sites left to the single-site entry
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int rc = ensure_init();
+        if (rc) return rc;
+        if (n_sites < 0 || H < 1 || W < 1 || (n_sites > 0 && !sites)) return fail(DCTP_E_INVALID, "dctp_score_accum_multi: n_sites=%d H=%d W=%d", n_sites, H, W);
+        for (int i = 0; i < n_sites; ++i) {
+            if (sites[i].B < 0 || sites[i].c_count < 0 || ((sites[i].B > 0 && sites[i].c_count > 0) && (!sites[i].x || !sites[i].accum)))
+                return fail(DCTP_E_INVALID, "dctp_score_accum_multi: site %d: B=%d c_count=%d or a null pointer", i, sites[i].B, sites[i].c_count);
+            if (static_cast<long long>(sites[i].B) * sites[i].c_count > (1ll << 30)) return fail(DCTP_E_INVALID, "too many maps in site %d", i);
+        }
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const bool kron = H == W && H <= 8 && g.kron_on, stack = H == W && g.stack_on && stack_shape_supported(H);
+        // one launch per SCORE_MAX_SEG sites; shapes the multi-site kernels do not take, and sites that are not 16-byte aligned,
+        // go through the single-site entry below
+        SiteDesc batch[SCORE_MAX_SEG];
+        int nb = 0;
+        for (int i = 0; i < n_sites; ++i) {
+            if (sites[i].B == 0 || sites[i].c_count == 0) continue;
+            if (!(kron || stack) || (reinterpret_cast<uintptr_t>(sites[i].x) % 16) != 0) { single.push_back(i); continue; }
+            batch[nb++] = SiteDesc{sites[i].x, sites[i].B, sites[i].c_count, sites[i].accum};
+            if (nb == SCORE_MAX_SEG || i == n_sites - 1) {
+                if ((rc = kron ? launch_kron(batch, nb, H, nullptr, nullptr, s) : launch_stack(batch, nb, H, nullptr, nullptr, s))) return rc;
+                nb = 0;
+            }
+        }
+        if (nb > 0 && (rc = kron ? launch_kron(batch, nb, H, nullptr, nullptr, s) : launch_stack(batch, nb, H, nullptr, nullptr, s))) return rc;
+    }
+    for (int i : single) {
+        const int rc = dctp_score_accum(sites[i].x, sites[i].B, H, W, static_cast<long long>(sites[i].c_count) * H * W, static_cast<long long>(H) * W, W, 0,
+                                        sites[i].c_count, sites[i].accum, nullptr, nullptr, DCTP_PATH_AUTO, stream);
+        if (rc) return rc;
+    }
+    return DCTP_OK;
 }
 
 int dctp_finalize(const double* accum, double n_images, float* out, int n, void* stream) {

@@ -25,22 +25,18 @@
 namespace dctp {
 
 struct KronArgs {
-    const float* x_dense;
-    long long total_elems;
-    int n_maps, c_count;
+    ScoreSegments seg;              // the activations of the launch (score_stack.cuh)
     int N, NN;
     int sub_tiles;                  // 128-map sub-tiles per TMA tile (1, 2 or 4)
     int row_floats;                 // shared-memory stride of a map's row in floats (EVEN: box width, ODD: NN)
     int tile_maps, num_tiles;
     uint32_t tile_bytes;            // bytes one TMA tile lands
     int box_rows;                   // second box dimension (EVEN: maps per tile, ODD: 128-byte rows per tile)
-    int tail_tile;                  // (ODD) tile converted straight from global memory, or -1
     uint32_t idesc;
     const uint8_t* k_hi;            // Kr operand images (StackSmem::LBO2 layout)
     const uint8_t* k_lo;
-    double* accum;
-    float* energy_out;
-    float* dump;
+    float* energy_out;              // optional, single-segment launches only
+    float* dump;                    // optional, single-segment launches only
     int* status;
 };
 
@@ -55,7 +51,7 @@ struct KronSmem {
 constexpr int KRON_NT = 320;
 
 template <int K2, bool EVEN>
-__global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_constant__ CUtensorMap tmap, const KronArgs a) {
+__global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_constant__ ScoreTensorMaps tmaps, const __grid_constant__ KronArgs a) {
     using S = KronSmem;
     using namespace umma;
     constexpr int KS = K2 / 16;
@@ -85,7 +81,7 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
         for (int s = 0; s < 4; ++s) { mbar_init(a_full + s, 4); mbar_init(a_free + s, 1); mbar_init(d_full + s, 1); mbar_init(d_free + s, 4); }
         mbar_init_fence();
     }
-    if (warp == 8 && lane == 0) tma_prefetch_desc(&tmap);
+    if (warp == 8 && lane == 0) tma_prefetch_desc(&tmaps.m[0]);
     fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -97,6 +93,12 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
 
     const int first = blockIdx.x, stride = gridDim.x;
     bool dead = false;
+    auto seg_of = [&](int tile, int& sg) {
+        while (tile >= a.seg.tile0[sg + 1]) ++sg;
+    };
+    auto is_tail = [&](int tile, int sg) {               // (ODD) a stream that does not end on a 128-byte row: last tile from global memory
+        return !EVEN && tile == a.seg.tile0[sg + 1] - 1 && (a.seg.total_elems[sg] & 31) != 0;
+    };
 #define KRON_WAIT(bar, par)                          \
     if (!mbar_wait((bar), (par))) {                  \
         dead = true;                                 \
@@ -107,12 +109,14 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
         // ================================================================ TMA producer
         if (elect_one()) {
             uint32_t it = 0;
+            int sg = 0;
             for (int tile = first; tile < a.num_tiles; tile += stride) {
-                if (tile == a.tail_tile) continue;
+                seg_of(tile, sg);
+                if (is_tail(tile, sg)) continue;
                 const uint32_t s = it % S::NSTG;
                 if (it >= S::NSTG) KRON_WAIT(stg_free + s, ((it / S::NSTG) - 1u) & 1u);
                 mbar_arrive_expect_tx(stg_full + s, a.tile_bytes);
-                tma_load_2d(stg + s * S::STG_STRIDE, &tmap, 0, tile * a.box_rows, stg_full + s);
+                tma_load_2d(stg + s * S::STG_STRIDE, &tmaps.m[sg], 0, (tile - a.seg.tile0[sg]) * a.box_rows, stg_full + s);
                 ++it;
             }
         }
@@ -145,8 +149,10 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
         // ================================================================ converters: thread = map, fp32 row -> bf16 hi | lo -> A (TMEM)
         const uint32_t lane_bits = (warp * 32u) << 16;
         uint32_t it = 0, j = 0;
+        int sg = 0;
         for (int tile = first; tile < a.num_tiles && !dead; tile += stride) {
-            const bool from_global = tile == a.tail_tile;
+            seg_of(tile, sg);
+            const bool from_global = is_tail(tile, sg);
             uint32_t s = 0;
             if (!from_global) {
                 s = it % S::NSTG;
@@ -158,9 +164,11 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
                 tc_fence_after_sync();
                 float v[K2];
                 if (from_global) {
-                    const long long e0 = (static_cast<long long>(tile) * a.tile_maps + st * 128 + tid) * a.NN;
+                    const long long e0 = (static_cast<long long>(tile - a.seg.tile0[sg]) * a.tile_maps + st * 128 + tid) * a.NN;
+                    const long long total = a.seg.total_elems[sg];
+                    const float* xs = a.seg.x[sg];
 #pragma unroll
-                    for (int i = 0; i < K2; ++i) v[i] = (i < a.NN && e0 + i < a.total_elems) ? a.x_dense[e0 + i] : 0.f;
+                    for (int i = 0; i < K2; ++i) v[i] = (i < a.NN && e0 + i < total) ? xs[e0 + i] : 0.f;
                 } else if constexpr (EVEN) {
                     const float4* row = reinterpret_cast<const float4*>(stg + s * S::STG_STRIDE) + static_cast<uint32_t>(st * 128 + tid) * (a.row_floats >> 2);
 #pragma unroll
@@ -201,12 +209,16 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
         const uint32_t et = tid - 128;
         const uint32_t lane_bits = ((warp & 3u) * 32u) << 16;
         uint32_t j = 0;
-        for (int tile = first; tile < a.num_tiles && !dead; tile += stride)
+        int sg = 0;
+        for (int tile = first; tile < a.num_tiles && !dead; tile += stride) {
+            seg_of(tile, sg);
+            const uint32_t C = static_cast<uint32_t>(a.seg.c_count[sg]), seg_maps = static_cast<uint32_t>(a.seg.n_maps[sg]);
+            double* const accum = a.seg.accum[sg];
             for (int st = 0; st < a.sub_tiles; ++st, ++j) {
                 const uint32_t sl = j & 3u;
                 KRON_WAIT(d_full + sl, (j >> 2) & 1u);
                 tc_fence_after_sync();
-                const long long m = static_cast<long long>(tile) * a.tile_maps + st * 128 + et;
+                const uint32_t m = static_cast<uint32_t>(tile - a.seg.tile0[sg]) * a.tile_maps + st * 128 + et;   // map within its segment
                 float e0 = 0.f, e1 = 0.f;
 #pragma unroll
                 for (int c = 0; c < K2; c += 16) {
@@ -218,25 +230,27 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
                         e0 = fmaf(__uint_as_float(z[i]), __uint_as_float(z[i]), e0);
                         e1 = fmaf(__uint_as_float(z[8 + i]), __uint_as_float(z[8 + i]), e1);
                     }
-                    if (a.dump != nullptr && m < a.n_maps)
+                    if (a.dump != nullptr && m < seg_maps)
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (c + i < a.NN) a.dump[m * a.NN + c + i] = __uint_as_float(z[i]);
+                            if (c + i < a.NN) a.dump[static_cast<long long>(m) * a.NN + c + i] = __uint_as_float(z[i]);
                 }
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_free + sl);
-                if (m < a.n_maps) {
+                if (m < seg_maps) {
                     const float e = e0 + e1;
-                    atomicAdd(a.accum + (static_cast<uint32_t>(m) % static_cast<uint32_t>(a.c_count)), static_cast<double>(e));
+                    atomicAdd(accum + (m % C), static_cast<double>(e));
                     if (a.energy_out) a.energy_out[m] = e;
                 }
             }
+        }
     }
 #undef KRON_WAIT
     if (dead) {
         atomicExch(a.status, DCTP_DEV_MMA_TIMEOUT);
-        for (int c = lane; c < a.c_count; c += 32) a.accum[c] = __longlong_as_double(0x7FF8000000000000ll);
+        for (int sgi = 0; sgi < a.seg.n_seg; ++sgi)
+            for (int c = lane; c < a.seg.c_count[sgi]; c += 32) a.seg.accum[sgi][c] = __longlong_as_double(0x7FF8000000000000ll);
     }
     tc_fence_before_sync();
     __syncthreads();

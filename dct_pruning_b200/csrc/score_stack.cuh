@@ -40,16 +40,26 @@
 
 namespace dctp {
 
+constexpr int SCORE_MAX_SEG = 16;   // activations (hook sites of the same map side) one launch can score
+
+// One dense activation of a launch: all its scored maps back to back.  A launch walks the tiles of its segments in order;
+// tile t belongs to segment s with tile0[s] <= t < tile0[s + 1].
+struct ScoreSegments {
+    int n_seg;
+    int tile0[SCORE_MAX_SEG + 1];
+    int n_maps[SCORE_MAX_SEG], c_count[SCORE_MAX_SEG];
+    long long total_elems[SCORE_MAX_SEG];                // n_maps * NN
+    const float* x[SCORE_MAX_SEG];                       // first scored element, 16-B aligned
+    double* accum[SCORE_MAX_SEG];                        // fp64 [c_count] of the site
+};
+struct ScoreTensorMaps { CUtensorMap m[SCORE_MAX_SEG]; };
+
 struct StackArgs {
-    const float* x_dense;           // first scored element; all scored maps back to back, 16-B aligned
-    long long total_elems;          // n_maps * NN
-    int n_maps, c_count;
+    ScoreSegments seg;
     int N, NN, Np;                  // map side, N*N, rows a map takes in Bx (= D1 columns per map): N rounded up to 8
     int G, MT;                      // maps per set and per tile (MT = G * J)
     int ncols;                      // G * Np = MMA N of stage 1
     int tile_elems, tile_rows, tile_vec, num_tiles;
-    int chan_step;                  // (gridDim.x * MT) mod c_count: channel advance between a CTA's consecutive tiles
-    int tail_tile;                  // tile converted straight from global memory (the stream does not end on a 128-byte row), or -1
     uint32_t idesc1, idesc2;
     uint32_t lbo1;                  // Bx: byte distance between consecutive 8-element k-chunks (2048 + 16 u, u chosen per side for conflict-free stores)
     const uint32_t* a_img;          // [128][32] packed bf16 pairs: the stacked basis as it sits in TMEM
@@ -57,9 +67,8 @@ struct StackArgs {
     const uint8_t* c2_lo;
     const uint16_t* table;          // [tile_vec] (VEC 4) / [2 * tile_vec] (VEC 2) byte offsets of a float4's pieces in Bx
     uint32_t table_bytes;
-    double* accum;
-    float* energy_out;
-    float* dump;
+    float* energy_out;              // optional, single-segment launches only: [n_maps] per-map energies
+    float* dump;                    // optional, single-segment launches only: coefficients
     int* status;
     long long* trace;               // bring-up aid (DCTP_S_TRACE): per role of CTA 0, cycles spent waiting / working
 };
@@ -87,7 +96,7 @@ struct StackSmem {
 // through a named barrier - the polls cost issue slots, the sleep behind mbarrier.try_wait being woken by any barrier event of
 // the CTA, but the extra hop costs more: 56x56 3.17 against 3.49 TB/s.)
 template <int KP, int VEC, int NCONV, int NE1G, int NCG>
-__global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_kernel(const __grid_constant__ CUtensorMap tmap, const StackArgs a) {
+__global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_kernel(const __grid_constant__ ScoreTensorMaps tmaps, const __grid_constant__ StackArgs a) {
     using S = StackSmem;
     using namespace umma;
     constexpr int J = KP <= 32 ? 64 / KP : 1;
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
         }
         mbar_init_fence();
     }
-    if (warp == W_PROD && lane == 0) tma_prefetch_desc(&tmap);
+    if (warp == W_PROD && lane == 0) tma_prefetch_desc(&tmaps.m[0]);
     fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -178,6 +187,14 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
     const int first = blockIdx.x, stride = gridDim.x;
     const uint32_t tile_bytes = static_cast<uint32_t>(a.tile_rows) * 128u;
     bool dead = false;
+    // segment of a tile: the roles walk the tiles in increasing order, so each keeps a cursor.  A segment whose stream does not
+    // end on a 128-byte row has its last tile converted straight from global memory (that row is not in the tensor map).
+    auto seg_of = [&](int tile, int& sg) {
+        while (tile >= a.seg.tile0[sg + 1]) ++sg;
+    };
+    auto is_tail = [&](int tile, int sg) {
+        return tile == a.seg.tile0[sg + 1] - 1 && (a.seg.total_elems[sg] & 31) != 0;
+    };
     // bring-up trace: one thread per role accumulates cycles in registers and writes them when its loop ends
     const bool tr_on = a.trace != nullptr && blockIdx.x == 0;
     bool tr_me = false;
@@ -191,14 +208,16 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
         if (elect_one()) {
             tr_me = tr_on;
             uint32_t it = 0;
+            int sg = 0;
             for (int tile = first; tile < a.num_tiles; tile += stride) {
-                if (tile == a.tail_tile) continue;
+                seg_of(tile, sg);
+                if (is_tail(tile, sg)) continue;
                 const uint32_t s = it % S::NSTG;
                 TR_START();
                 if (it >= S::NSTG && !mbar_wait(stg_free + s, ((it / S::NSTG) - 1u) & 1u)) { dead = true; break; }
                 TR_ADD(tr0);
                 mbar_arrive_expect_tx(stg_full + s, tile_bytes);
-                tma_load_2d(stg + s * S::STG_STRIDE, &tmap, 0, tile * a.tile_rows, stg_full + s);
+                tma_load_2d(stg + s * S::STG_STRIDE, &tmaps.m[sg], 0, (tile - a.seg.tile0[sg]) * a.tile_rows, stg_full + s);
                 ++it;
             }
             TR_FLUSH(0);
@@ -273,16 +292,23 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
     } else if (warp < W_E1) {
         // ================================================================ converters: fp32 tile -> bf16 hi/lo -> Bx
         const uint32_t cg = warp / (NCONV / NCG), ctid = tid - cg * NCT;     // converter group, thread within it
-        uint32_t n = cg;                                                   // this CTA's tile number (= its TMA sequence number: only the
-        tr_me = tr_on && tid == 0;                                         //  CTA's last tile can be the one converted from global memory)
-        for (int tile = first + (int)cg * stride; tile < a.num_tiles; tile += NCG * stride, n += NCG) {
-            const uint32_t b = n & 1u, s = n % S::NSTG, it = n;
+        uint32_t n = 0, it = 0;                                            // the CTA's tile number / its TMA sequence number
+        int sg = 0;
+        tr_me = tr_on && tid == 0;
+        for (int tile = first; tile < a.num_tiles; tile += stride, ++n) {
+            seg_of(tile, sg);
+            const bool tail = is_tail(tile, sg);
+            if (n % NCG != cg) {                                           // the other group's tile: only keep the TMA count in step
+                if (!tail) ++it;
+                continue;
+            }
+            const uint32_t b = n & 1u, s = it % S::NSTG;
             TR_START();
             {
                 bool ok = true;
                 if (n >= 2) ok = mbar_wait(bx_free + b, ((n >> 1) - 1u) & 1u);
                 TR_ADD(tr0);
-                if (ok && tile != a.tail_tile) ok = mbar_wait(stg_full + s, (it / S::NSTG) & 1u);
+                if (ok && !tail) ok = mbar_wait(stg_full + s, (it / S::NSTG) & 1u);
                 TR_ADD(tr1);
                 if (!ok) { dead = true; break; }
             }
@@ -306,7 +332,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
             auto entry = [&](int f) {
                 return VEC == 4 ? static_cast<uint32_t>(reinterpret_cast<const uint16_t*>(tab)[f]) : reinterpret_cast<const uint32_t*>(tab)[f];
             };
-            if (tile != a.tail_tile) {
+            if (!tail) {
                 const float4* src = reinterpret_cast<const float4*>(stg + s * S::STG_STRIDE);
                 // CB vectors (and their table entries) are loaded before the first store: the stores go to shared memory
                 // too, so the compiler cannot hoist a later iteration's loads above them by itself
@@ -336,15 +362,17 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
                 TR_ADD(tr2);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(stg_free + s);
+                ++it;
             } else {                                                      // the stream's last, partial 128-byte row is not in the tensor map
-                const long long e0 = static_cast<long long>(tile) * a.tile_elems;
+                const long long e0 = static_cast<long long>(tile - a.seg.tile0[sg]) * a.tile_elems, total = a.seg.total_elems[sg];
+                const float* xs = a.seg.x[sg];
                 for (int f = ctid; f < a.tile_vec; f += NCT) {
                     const long long e = e0 + 4ll * f;
                     float4 v;
-                    v.x = e + 0 < a.total_elems ? a.x_dense[e + 0] : 0.f;
-                    v.y = e + 1 < a.total_elems ? a.x_dense[e + 1] : 0.f;
-                    v.z = e + 2 < a.total_elems ? a.x_dense[e + 2] : 0.f;
-                    v.w = e + 3 < a.total_elems ? a.x_dense[e + 3] : 0.f;
+                    v.x = e + 0 < total ? xs[e + 0] : 0.f;
+                    v.y = e + 1 < total ? xs[e + 1] : 0.f;
+                    v.z = e + 2 < total ? xs[e + 2] : 0.f;
+                    v.w = e + 3 < total ? xs[e + 3] : 0.f;
                     emit(entry(f), v);
                 }
             }
@@ -442,12 +470,13 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
         const uint32_t s = lane >> 4, r = lane & 15u;
         const uint32_t my_set = J == 4 ? q : J == 2 ? (q >> 1) : 0u;
         const uint32_t my_v = J == 4 ? r : J == 2 ? 16u * (q & 1u) + r : 16u * q + r;
-        const uint32_t C = static_cast<uint32_t>(a.c_count);
         uint32_t n = 0;
-        // channel of the first map of the CTA's current tile, advanced without a division (n_maps < 2^30: 32-bit arithmetic)
-        uint32_t chan0 = (static_cast<uint32_t>(first) * a.MT) % C;
+        int sg = 0;
         tr_me = tr_on && warp == W_E2 && lane == 0;
         for (int tile = first; tile < a.num_tiles; tile += stride, ++n) {
+            seg_of(tile, sg);
+            const uint32_t C = static_cast<uint32_t>(a.seg.c_count[sg]), seg_maps = static_cast<uint32_t>(a.seg.n_maps[sg]);
+            double* const accum = a.seg.accum[sg];
             const uint32_t b2 = nb2 == 2 ? (n & 1u) : 0u, use2 = nb2 == 2 ? (n >> 1) : n;
             TR_START();
             {
@@ -458,7 +487,8 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
             }
             tc_fence_after_sync();
             const uint32_t d2 = tmem + TM_D2 + b2 * 64 + lane_q;
-            const uint32_t m0 = static_cast<uint32_t>(tile) * a.MT;
+            const uint32_t m0 = static_cast<uint32_t>(tile - a.seg.tile0[sg]) * a.MT;      // first map of the tile within its segment
+            const uint32_t chan0 = m0 % C;                                 // (n_maps < 2^30: 32-bit arithmetic)
             float e[T2];
             // the lane's T2 * KP (64 or 48) coefficients in two round trips of at most 32 registers; D2 is handed back as soon
             // as the second one has landed
@@ -496,7 +526,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
                         if (a.dump != nullptr) {
                             const uint32_t m = m0 + (2 * t + s) * J + my_set;
                             const int u0 = (c0 + c) - t * KP;
-                            if (m < (uint32_t)a.n_maps && my_v < (uint32_t)a.N)
+                            if (m < seg_maps && my_v < (uint32_t)a.N)
 #pragma unroll
                                 for (int i = 0; i < 16; ++i)
                                     if (u0 + i < a.N) a.dump[static_cast<long long>(m) * a.NN + (u0 + i) * a.N + my_v] = __uint_as_float(z[c + i]);
@@ -526,10 +556,10 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
                 }
                 if (lane < 2u * T2) {
                     const uint32_t ml = lane * J + my_set;                 // map (g = 2t + s = lane, my_set) of the tile
-                    if (m0 + ml < (uint32_t)a.n_maps) {
+                    if (m0 + ml < seg_maps) {
                         uint32_t ch = chan0 + ml;
                         while (ch >= C) ch -= C;
-                        atomicAdd(a.accum + ch, static_cast<double>(mine));
+                        atomicAdd(accum + ch, static_cast<double>(mine));
                     }
                 }
             } else {
@@ -546,16 +576,14 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
                     else if (J == 2) en = red_w[(2 * set) * 8 + g] + red_w[(2 * set + 1) * 8 + g];
                     else en = (red_w[g] + red_w[8 + g]) + (red_w[16 + g] + red_w[24 + g]);
                     const uint32_t m = m0 + et;
-                    if (m < (uint32_t)a.n_maps) {
+                    if (m < seg_maps) {
                         uint32_t ch = chan0 + et;
                         while (ch >= C) ch -= C;
-                        atomicAdd(a.accum + ch, static_cast<double>(en));
+                        atomicAdd(accum + ch, static_cast<double>(en));
                         a.energy_out[m] = en;
                     }
                 }
             }
-            chan0 += a.chan_step;
-            if (chan0 >= C) chan0 -= C;
             TR_ADD(tr1);
         }
         TR_FLUSH(32);
@@ -565,7 +593,8 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
 #undef TR_FLUSH
     if (dead) {                                                           // a hand-over never came: flag it and poison the result
         atomicExch(a.status, DCTP_DEV_MMA_TIMEOUT);
-        for (int c = lane; c < a.c_count; c += 32) a.accum[c] = __longlong_as_double(0x7FF8000000000000ll);
+        for (int sgi = 0; sgi < a.seg.n_seg; ++sgi)
+            for (int c = lane; c < a.seg.c_count[sgi]; c += 32) a.seg.accum[sgi][c] = __longlong_as_double(0x7FF8000000000000ll);
     }
     tc_fence_before_sync();
     __syncthreads();

@@ -79,6 +79,22 @@ int dctp_score_accum(const float* x, int B, int H, int W,
                      double* accum, float* energy_out, float* coeff_out,
                      int path, void* stream);
 
+/* Several hook sites in ONE launch.  The forward pass of the CIFAR nets and of U^2-Netp's small stages fires tens of hooks on
+ * activations of a few MB; scored one by one they are bound by the host's launch rate (~12 us per hook), not by the GPU.  The host
+ * side may therefore hold on to a run of activations of the same map size and hand them over together
+ * (dct_pruning_b200.hooks.ScoreSession does: the deferred form of get_feature_hook, utils/common.py:262-277, one call per run of
+ * same-sized sites instead of one per site).  Every site is DENSE: x points at its first scored map (the channel window already
+ * applied) and B * c_count maps of H x W floats follow back to back; accum as in dctp_score_accum.  Map sizes the multi-site
+ * kernels take (square, side <= 8, or even side 10..64 - above 32 a multiple of 4) are scored SCORE_MAX_SEG = 16 sites per launch;
+ * any other shape falls back to one launch per site.  Results are identical to n_sites dctp_score_accum calls. */
+typedef struct dctp_site {
+    const float* x;
+    double* accum;
+    int B;
+    int c_count;
+} dctp_site;
+int dctp_score_accum_multi(const dctp_site* sites, int n_sites, int H, int W, void* stream);
+
 /* out[i] = (float)(accum[i] / n_images).  Replaces the running mean over images
  * (utils/common.py:275-277) and the fp32 vector np.save writes (:394). */
 int dctp_finalize(const double* accum, double n_images, float* out, int n, void* stream);

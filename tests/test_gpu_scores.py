@@ -157,3 +157,39 @@ def test_cuda_graph_replay_matches_eager(lib, cuda_device):
     assert sorted(got) == sorted(want) and graphed.n_images == 48
     for stem in want:
         np.testing.assert_allclose(got[stem], want[stem], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize('net_name,batch,side', [('resnet_56', 16, 32), ('vgg_16_bn', 8, 32), ('googlenet', 4, 32), ('densenet_40', 4, 32),
+                                                 ('resnet_50', 2, 224), ('u2netp', 2, 160)])
+def test_multi_site_launches_match_one_launch_per_site(lib, cuda_device, net_name, batch, side):
+    """Small activations are held and scored up to 16 sites per launch (dctp_score_accum_multi).  Same numbers as one launch per
+    site (fp64 sums in another order: 1e-12), far fewer launches, and no held activation was overwritten before it was read."""
+    from dct_pruning_b200.generate import synthetic_batches
+    from dct_pruning_b200.hooks import ScoreSession
+    from dct_pruning_b200.zoo import get_network
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    torch.manual_seed(0)
+    net = get_network(net_name).to(cuda_device).eval()
+    batches = [(_images(b)).to(cuda_device) for b in synthetic_batches(batch, side, 2, as_dict=(net_name == 'u2netp'))]
+    out, launches = {}, {}
+    for mode, defer in (('per_site', 0), ('batched', None)):
+        session = ScoreSession(net, net_name, defer_bytes=defer)
+        n0 = lib.dctp_launch_count()
+        with session, torch.no_grad():
+            for x in batches:
+                net(x)
+        out[mode] = session.finalize()
+        launches[mode] = lib.dctp_launch_count() - n0
+    assert sorted(out['batched']) == sorted(out['per_site'])
+    for stem in out['per_site']:
+        np.testing.assert_allclose(out['batched'][stem], out['per_site'][stem], rtol=1e-6, atol=0, err_msg=stem)
+        assert ((out['batched'][stem] == 0) == (out['per_site'][stem] == 0)).all()
+    # (DenseNet's 12-channel windows of a batch are not one dense stream: only its three full-width sites can be held)
+    assert launches['batched'] < launches['per_site'] or net_name == 'densenet_40'
+    assert launches['batched'] <= launches['per_site']
+
+
+def _images(sample):
+    from dct_pruning_b200.generate import _images_of
+    return _images_of(sample)
