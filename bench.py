@@ -335,7 +335,11 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tab = json.load(f)
-            prefix = dom_name.split('<')[0]
+            # traffic.json is keyed by the demangled instantiation (score_stack_kernel<64,4,8,1,2>); the library's label names
+            # the same first template argument (KP=64 / K2=64): match on kernel + that argument
+            import re
+            mm = re.match(r'(\w+)(?:<(?:[A-Z0-9]+=)?(\d+))?', dom_name)
+            prefix = mm.group(1) + ('<' + mm.group(2) + ',' if mm.group(2) else '')
             hits = [v for k, v in tab.items() if isinstance(v, dict) and k.startswith(prefix)]
             if hits:
                 traffic = sum(v['dram_bytes_per_launch'] * v['launches'] for v in hits) / sum(v['launches'] for v in hits)
@@ -525,7 +529,7 @@ def run_ours(args):
                        'parallelism': 'batch-sharded x%d, 1 all-reduce per run' % world,
                        'peaks': {'hbm_gbs': hbm_peak, 'bf16_tflops_sustained': tflops, 'kind': peak_kind}},
             'gpu_launches': main['gpu_launches'],
-            'launch_batching': 'activations below %d MB are held and scored up to 16 sites per launch (dctp_score_accum_multi)' % (64),
+            'launch_batching': 'activations below 32 MB are held and scored up to 16 sites per launch (dctp_score_accum_multi)',
             'roofline': main.get('roofline'),
             'hook_path_GBps': main['hook_path_GBps'],
             'binding_roofline_frac': main['binding_roofline_frac'],

@@ -65,7 +65,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise ImportError('libdctp.so not found at %s: run `python -c "import __graft_entry__ as g; g.build()"` '
                           '(or python -m dct_pruning_b200.build); there is no CPU fallback' % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(os.environ.get('DCTP_LIB', LIB_PATH))     # (DCTP_LIB: an alternative build, for A/B measurements)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = the .so is stale w.r.t. include/dctp.h
         fn.restype, fn.argtypes = res, args

@@ -24,18 +24,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_init_fence() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// One probe; the thread is suspended in hardware (no issue slots burnt) until the phase completes or
-// `suspend_ns` has passed, whichever is first.
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t suspend_ns = 20000u) {
+// One probe: mbarrier.try_wait blocks in hardware until the phase completes or an implementation-defined time limit passes.
+// (No suspend-time hint: with one, ptxas follows the probe with NANOSLEEP.SYNCS, which any barrier event of the CTA wakes up - in
+//  a warp-specialised kernel with a barrier event every few hundred cycles the waiting warps then spin through ~10 instructions
+//  per event: 40 % of the instructions score_stack_kernel executed, profiles/r02_ncu_stack_56x56.md.  Measured on one box, same
+//  build otherwise: without the hint 56x56 3.71 vs 3.67 TB/s, 28x28 3.41 vs 3.35; a nanosleep of 20 or 60 ns between probes changes
+//  nothing: the polls are not what bounds these kernels.)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(suspend_ns)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
 }
@@ -53,8 +57,9 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
     for (;;) {
 #pragma unroll 1
-        for (int spin = 0; spin < 16; ++spin)
+        for (int spin = 0; spin < 16; ++spin) {
             if (mbar_try_wait(bar, parity)) return true;
+        }
         if (global_ns() - t0 > 2000000000ull) return false;
     }
 }

@@ -28,7 +28,8 @@ class ScoreSession:
     # the GPU.  Activations smaller than DEFER_BYTES are therefore held (a reference keeps them alive, nothing is copied) and
     # scored together with other sites of the same map size in ONE launch (dctp_score_accum_multi, up to 16 sites): ResNet-56's
     # 55 hooks become 6 launches, U^2-Netp's 118 about 30.  One group is kept per map size (U^2-Net's stages alternate sizes);
-    # a group is launched when it is full, everything at the end of the run, when HELD_BYTES are held, or on flush().
+    # a group is launched when it is full; everything that is held at the end of the forward pass (a hook on the net itself), when
+    # HELD_BYTES are held, and on flush().
     # Larger activations are scored at once, as before.
     DEFER_BYTES = 32 << 20
     MAX_PENDING = 16
@@ -67,6 +68,9 @@ class ScoreSession:
         for idx, site in enumerate(self.sites):
             module = resolve_module(self.net, site.module)
             self.handles.append(module.register_forward_hook(self._make_hook(idx, site)))
+        # held activations are scored when the forward pass they belong to ends: nothing is kept across batches, so the caching
+        # allocator sees the same allocation pattern every step
+        self.handles.append(self.net.register_forward_hook(lambda module, inputs, output: self.flush()))
         return self
 
     def remove(self):
