@@ -396,17 +396,20 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
             # the hooks' own share, in line: one more pass with an event pair around every hook launch inside the forward
             session.reset()
             pairs = []
-            plain_score = session.score
+            raw_single, raw_multi = session._score_accum, session._score_multi
 
-            def timed_score(idx, t):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                plain_score(idx, t)
-                b.record()
-                pairs.append((a, b))
-            session.score = timed_score
+            def timed(fn):
+                def call(*a):
+                    e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e_a.record()
+                    rc = fn(*a)
+                    e_b.record()
+                    pairs.append((e_a, e_b))
+                    return rc
+                return call
+            session._score_accum, session._score_multi = timed(raw_single), timed(raw_multi)      # the two launch points
             e2e_steps(1)
-            session.score = plain_score
+            session._score_accum, session._score_multi = raw_single, raw_multi
             torch.cuda.synchronize()
             hooks_ms = sum(a.elapsed_time(b) for a, b in pairs)
         # the same loop without hooks (accumulator still copied out), for the breakdown
@@ -425,7 +428,7 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
                       'score_checksum': float(host_scores.double().sum()), 'cuda_graph': bool(args.graph),
                       'includes': 'H2D of every batch from pinned memory, fp32 cuDNN forward with all hooks live, D2H of the running sums every '
                                   'step; once per run: all-reduce, finalise, top-k, D2H of the scores, np.save of every score file (rank 0)',
-                      'hooks_in_line_how': 'CUDA event pair around every hook launch inside one extra forward pass (not the timed one)'}
+                      'hooks_in_line_how': 'CUDA event pair around every score launch (single-site and multi-site) inside one extra forward pass (not the timed one)'}
     out['_acts_cpu'] = [acts[i][:4].cpu() for i in live] if (rank == 0 and world == 1 and net_name == args.net and not args.no_cpu_baseline) else None
     out['_acts'] = acts if out['_acts_cpu'] is not None else None
     out['_sites'] = session.sites
@@ -529,7 +532,7 @@ def run_ours(args):
                        'parallelism': 'batch-sharded x%d, 1 all-reduce per run' % world,
                        'peaks': {'hbm_gbs': hbm_peak, 'bf16_tflops_sustained': tflops, 'kind': peak_kind}},
             'gpu_launches': main['gpu_launches'],
-            'launch_batching': 'activations below 32 MB are held and scored up to 16 sites per launch (dctp_score_accum_multi)',
+            'launch_batching': 'activations below 1 GB are held and scored up to 16 sites of a map size per launch (dctp_score_accum_multi); by_kernel / by_shape time one launch per site',
             'roofline': main.get('roofline'),
             'hook_path_GBps': main['hook_path_GBps'],
             'binding_roofline_frac': main['binding_roofline_frac'],

@@ -24,16 +24,18 @@ from .sites import DENSENET_WINDOW, VARIANT_INPUT, VARIANT_LAST12, hook_sites, r
 
 
 class ScoreSession:
-    # Hook launches of a few MB are bound by the host's launch rate (~12 us per hook through Python, ctypes and the driver), not by
-    # the GPU.  Activations smaller than DEFER_BYTES are therefore held (a reference keeps them alive, nothing is copied) and
-    # scored together with other sites of the same map size in ONE launch (dctp_score_accum_multi, up to 16 sites): ResNet-56's
-    # 55 hooks become 6 launches, U^2-Netp's 118 about 30.  One group is kept per map size (U^2-Net's stages alternate sizes);
-    # a group is launched when it is full; everything that is held at the end of the forward pass (a hook on the net itself), when
-    # HELD_BYTES are held, and on flush().
-    # Larger activations are scored at once, as before.
-    DEFER_BYTES = 32 << 20
+    # One launch per hook costs twice.  The host needs ~12 us per hook (Python, ctypes, driver), which bounds the CIFAR nets and
+    # U^2-Netp's small stages; and every launch of the warp-specialised kernels pays ~8-10 us of prologue, pipeline fill and drain
+    # on the GPU (profiles/r02_launches_bench_resnet50.csv: 10 us + bytes / 3.6 TB/s), 15 % of ResNet-50's step.  Activations
+    # smaller than DEFER_BYTES are therefore held (a reference keeps them alive, nothing is copied) and scored together with the
+    # other sites of the same map size in ONE launch (dctp_score_accum_multi, up to 16 sites): ResNet-50's 49 hooks become 8
+    # launches, ResNet-56's 55 become 6, U^2-Netp's 118 about 25.  One group is kept per map size (U^2-Net's stages alternate
+    # sizes); a group is launched when it is full; everything that is held at the end of the forward pass (a hook on the net
+    # itself), when HELD_BYTES are held, and on flush().  The price is memory: up to HELD_BYTES of activations stay allocated
+    # until their launch (ResNet-50 at batch 256: 4.3 GB for the ten 56x56 sites).  defer_bytes=0 restores one launch per hook.
+    DEFER_BYTES = 1 << 30
     MAX_PENDING = 16
-    HELD_BYTES = 2 << 30
+    HELD_BYTES = 8 << 30
 
     def __init__(self, net, net_name, path='auto', capacity=1 << 18, sites=None, defer_bytes=None):
         self.net = net
