@@ -71,10 +71,7 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
     uint64_t* d_free = bars + 18;         // [4] 4 epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_SLOT);
 
-    for (uint32_t off = tid * 16; off < HALF; off += KRON_NT * 16) {
-        *reinterpret_cast<uint4*>(kr + off) = *reinterpret_cast<const uint4*>(a.k_hi + off);
-        *reinterpret_cast<uint4*>(kr + HALF + off) = *reinterpret_cast<const uint4*>(a.k_lo + off);
-    }
+    // barriers and TMEM first: the producer warp then has tiles on their way while the other warps stage the Kronecker basis
     if (warp == 9) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         for (int s = 0; s < 3; ++s) { mbar_init(stg_full + s, 1); mbar_init(stg_free + s, 4); }
@@ -82,13 +79,20 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
         mbar_init_fence();
     }
     if (warp == 8 && lane == 0) tma_prefetch_desc(&tmaps.m[0]);
-    fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-
     launch_dependents();
+    if (warp != 8) {
+        const uint32_t ptid = tid < 256 ? tid : tid - 32;
+        for (uint32_t off = ptid * 16; off < HALF; off += (KRON_NT - 32) * 16) {
+            *reinterpret_cast<uint4*>(kr + off) = *reinterpret_cast<const uint4*>(a.k_hi + off);
+            *reinterpret_cast<uint4*>(kr + HALF + off) = *reinterpret_cast<const uint4*>(a.k_lo + off);
+        }
+        fence_async_smem();
+        named_bar_sync(6, KRON_NT - 32);
+    }
     grid_dependency_wait();
 
     const int first = blockIdx.x, stride = gridDim.x;

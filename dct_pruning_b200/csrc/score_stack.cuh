@@ -131,14 +131,8 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
     uint64_t* d2_free = bars + 20;                                        // [2] 4 epilogue-2 warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_SLOT);
 
-    // ---- prologue (independent of the activation: overlaps the preceding kernel under a dependent launch)
-    for (uint32_t off = tid * 16; off < 4 * S::BX_HALF; off += NT * 16) *reinterpret_cast<uint4*>(bx + off) = make_uint4(0, 0, 0, 0);
-    for (uint32_t off = tid * 16; off < S::C2_HALF; off += NT * 16) {
-        *reinterpret_cast<uint4*>(c2 + off) = *reinterpret_cast<const uint4*>(a.c2_hi + off);
-        *reinterpret_cast<uint4*>(c2 + S::C2_HALF + off) = *reinterpret_cast<const uint4*>(a.c2_lo + off);
-    }
-    for (uint32_t off = tid * 16; off < a.table_bytes; off += NT * 16)
-        *reinterpret_cast<uint4*>(smem + S::OFF_TABLE + off) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.table) + off);
+    // ---- prologue (independent of the activation).  Barriers and TMEM first: once they exist the producer warp goes ahead and has
+    //      the first three tiles on their way from HBM while the other warps stage the bases and zero the operand buffers.
     if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         for (int s = 0; s < 3; ++s) { mbar_init(stg_full + s, 1); mbar_init(stg_free + s, NCONV / NCG); }
@@ -151,37 +145,47 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
         mbar_init_fence();
     }
     if (warp == W_PROD && lane == 0) tma_prefetch_desc(&tmaps.m[0]);
-    fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    if (warp < 4) {                                                       // the stacked basis -> TMEM columns [0,32)
-        uint32_t v[16];
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-            const uint4* src = reinterpret_cast<const uint4*>(a.a_img + tid * 32 + part * 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint4 q4 = src[i];
-                v[4 * i] = q4.x; v[4 * i + 1] = q4.y; v[4 * i + 2] = q4.z; v[4 * i + 3] = q4.w;
-            }
-            tmem_st16(tmem + ((warp * 32u) << 16) + TM_A + part * 16, v);
-        }
-        tmem_st_wait();
-    } else if (warp < 8) {                                                // A2 (both buffers): columns a tile never writes stay zero
-        uint32_t z[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) z[i] = 0u;
-#pragma unroll
-        for (int part = 0; part < 8; ++part) tmem_st16(tmem + (((warp & 3u) * 32u) << 16) + TM_A2 + part * 16, z);
-        tmem_st_wait();
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-
     launch_dependents();                                                  // this CTA holds its TMEM columns (see score_umma.cuh)
+    if (warp != W_PROD) {
+        const uint32_t ptid = tid < W_PROD * 32 ? tid : tid - 32;          // thread index among the NT - 32 staging threads
+        constexpr uint32_t PNT = NT - 32;
+        for (uint32_t off = ptid * 16; off < 4 * S::BX_HALF; off += PNT * 16) *reinterpret_cast<uint4*>(bx + off) = make_uint4(0, 0, 0, 0);
+        for (uint32_t off = ptid * 16; off < S::C2_HALF; off += PNT * 16) {
+            *reinterpret_cast<uint4*>(c2 + off) = *reinterpret_cast<const uint4*>(a.c2_hi + off);
+            *reinterpret_cast<uint4*>(c2 + S::C2_HALF + off) = *reinterpret_cast<const uint4*>(a.c2_lo + off);
+        }
+        for (uint32_t off = ptid * 16; off < a.table_bytes; off += PNT * 16)
+            *reinterpret_cast<uint4*>(smem + S::OFF_TABLE + off) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.table) + off);
+        if (warp < 4) {                                                   // the stacked basis -> TMEM columns [0,32)
+            uint32_t v[16];
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.a_img + tid * 32 + part * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 q4 = src[i];
+                    v[4 * i] = q4.x; v[4 * i + 1] = q4.y; v[4 * i + 2] = q4.z; v[4 * i + 3] = q4.w;
+                }
+                tmem_st16(tmem + ((warp * 32u) << 16) + TM_A + part * 16, v);
+            }
+            tmem_st_wait();
+        } else if (warp < 8) {                                            // A2 (both buffers): columns a tile never writes stay zero
+            uint32_t z[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+            for (int part = 0; part < 8; ++part) tmem_st16(tmem + (((warp & 3u) * 32u) << 16) + TM_A2 + part * 16, z);
+            tmem_st_wait();
+        }
+        fence_async_smem();
+        tc_fence_before_sync();
+        named_bar_sync(6, NT - 32);                                       // every warp but the producer
+        tc_fence_after_sync();
+    }
     grid_dependency_wait();                                               // the activation is complete
 
     const int first = blockIdx.x, stride = gridDim.x;
