@@ -78,7 +78,7 @@ struct State {
     std::map<int, StackBasis> stack;                   // N
     std::map<int, KronBasis> kron;                     // N
     bool kron_on = true;                               // AUTO routes dense sides <= 8 to the Kronecker kernel (DCTP_KRON=0: round-1 kernels)
-    int stack_cfg = 0;                                 // role layout of the stacked-basis kernel (DCTP_STACK_CFG, see stack_kernel_fn)
+    int stack_cfg = 4;                                 // role layout of the stacked-basis kernel (DCTP_STACK_CFG, see stack_kernel_fn)
     bool stack_on = true;                              // AUTO routes dense even sides to the stacked-basis kernel (DCTP_STACK=0: round-1 kernels)
     long long stack_min_bytes = 0;                     // ... for launches of at least this many bytes (DCTP_STACK_MIN_MB)
     void* encode_tiled = nullptr;                      // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link dependency)
@@ -298,31 +298,38 @@ int get_stack_basis(int N, StackBasis& out) {
 }
 
 // instantiations: variant v = (KP 16, VEC 4), (16, 2), (32, 4), (32, 2), (48, 4), (64, 4); configuration cfg = role layout
-//   cfg 0 (default): 8 converter warps in two groups (alternate tiles), one epilogue-1 group, 23 warps
+//   cfg 0: 8 converter warps in two groups (alternate tiles), one epilogue-1 group, 23 warps
 //   cfg 1: the same with two epilogue-1 groups, 31 warps            cfg 2: 4 converter warps in one group, 19 warps
+//   cfg 3: 4 converter warps in two groups, two epilogue-1 and two epilogue-2 groups, 31 warps      cfg 4 (default): cfg 0 with two epilogue-2 groups, 27 warps
+// same box, cfg 0 / cfg 4: 56x56 3.73 / 3.73, 28x28 3.47 / 3.62, 14x14 3.19 / 3.25 TB/s; cfg 3 3.49 at 56x56
 // measured on B200, [256,C,N,N] 56x56 / 28x28 / 14x14, TB/s: cfg 0 3.85 / 3.67 / 3.26, cfg 1 3.78 / 3.57 / 3.12, cfg 2 3.59 / 3.31 / 2.89
-constexpr int STACK_CFGS = 3;
+constexpr int STACK_CFGS = 5;
 typedef void (*StackKernel)(const ScoreTensorMaps, const StackArgs);
-template <int NCONV, int NE1G, int NCG>
+template <int NCONV, int NE1G, int NCG, int NE2G = 1>
 StackKernel stack_kernel_of(int v) {
     switch (v) {
-        case 0: return score_stack_kernel<16, 4, NCONV, NE1G, NCG>;
-        case 1: return score_stack_kernel<16, 2, NCONV, NE1G, NCG>;
-        case 2: return score_stack_kernel<32, 4, NCONV, NE1G, NCG>;
-        case 3: return score_stack_kernel<32, 2, NCONV, NE1G, NCG>;
-        case 4: return score_stack_kernel<48, 4, NCONV, NE1G, NCG>;
-        default: return score_stack_kernel<64, 4, NCONV, NE1G, NCG>;
+        case 0: return score_stack_kernel<16, 4, NCONV, NE1G, NCG, NE2G>;
+        case 1: return score_stack_kernel<16, 2, NCONV, NE1G, NCG, NE2G>;
+        case 2: return score_stack_kernel<32, 4, NCONV, NE1G, NCG, NE2G>;
+        case 3: return score_stack_kernel<32, 2, NCONV, NE1G, NCG, NE2G>;
+        case 4: return score_stack_kernel<48, 4, NCONV, NE1G, NCG, NE2G>;
+        default: return score_stack_kernel<64, 4, NCONV, NE1G, NCG, NE2G>;
     }
 }
 StackKernel stack_kernel_fn(int cfg, int v) {
     switch (cfg) {
         case 1: return stack_kernel_of<8, 2, 2>(v);
         case 2: return stack_kernel_of<4, 1, 1>(v);
+        case 3: return stack_kernel_of<4, 2, 2, 2>(v);
+        case 4: return stack_kernel_of<8, 1, 2, 2>(v);
         default: return stack_kernel_of<8, 1, 2>(v);
     }
 }
 const void* stack_kernel_ptr(int cfg, int v) { return reinterpret_cast<const void*>(stack_kernel_fn(cfg, v)); }
-int stack_threads(int cfg) { return cfg == 1 ? (8 + 16 + 7) * 32 : cfg == 2 ? (4 + 8 + 7) * 32 : (8 + 8 + 7) * 32; }
+int stack_threads(int cfg) {
+    static const int warps[STACK_CFGS] = {8 + 8 + 4 + 3, 8 + 16 + 4 + 3, 4 + 8 + 4 + 3, 4 + 16 + 8 + 3, 8 + 8 + 8 + 3};
+    return warps[cfg] * 32;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -673,7 +680,7 @@ int ensure_init() {
         if (!g.encode_tiled) return fail(DCTP_E_CUDA, "the driver does not export cuTensorMapEncodeTiled");
     }
     if (const char* e = std::getenv("DCTP_KRON")) g.kron_on = std::atoi(e) != 0;
-    if (const char* e = std::getenv("DCTP_STACK_CFG")) { g.stack_cfg = std::atoi(e); if (g.stack_cfg < 0 || g.stack_cfg >= STACK_CFGS) g.stack_cfg = 0; }
+    if (const char* e = std::getenv("DCTP_STACK_CFG")) { g.stack_cfg = std::atoi(e); if (g.stack_cfg < 0 || g.stack_cfg >= STACK_CFGS) g.stack_cfg = 4; }
     if (const char* e = std::getenv("DCTP_STACK")) g.stack_on = std::atoi(e) != 0;
     if (const char* e = std::getenv("DCTP_STACK_MIN_MB")) g.stack_min_bytes = static_cast<long long>(std::atoi(e)) << 20;
     if (const char* e = std::getenv("DCTP_TP")) g.t_prod = std::atoi(e) != 0;

@@ -40,6 +40,9 @@
 
 namespace dctp {
 
+#ifndef STACK_E1_BATCH
+#define STACK_E1_BATCH 4           // 8-column groups of D1 an epilogue-1 warp requests per TMEM round trip
+#endif
 constexpr int SCORE_MAX_SEG = 16;   // activations (hook sites of the same map side) one launch can score
 
 // One dense activation of a launch: all its scored maps back to back.  A launch walks the tiles of its segments in order;
@@ -91,18 +94,19 @@ struct StackSmem {
 
 
 // KP: contraction length per map (N rounded up to 16); VEC: granularity of a row in the fp32 stream (4: N % 4 == 0, 2: N even)
-// NCONV: converter warps (4 or 8) in NCG groups (group g converts the CTA's tiles g, g + NCG, ...); NE1G: epilogue-1 groups (1 or 2).
+// NCONV: converter warps (4 or 8) in NCG groups (group g converts the CTA's tiles g, g + NCG, ...); NE1G / NE2G: epilogue-1 / epilogue-2
+// groups (1 or 2; group g takes the CTA's tiles g, g + 2, ...).
 // Every warp polls the mbarriers it depends on itself.  (Measured and dropped: one polling warp per role releasing its siblings
 // through a named barrier - the polls cost issue slots, the sleep behind mbarrier.try_wait being woken by any barrier event of
 // the CTA, but the extra hop costs more: 56x56 3.17 against 3.49 TB/s.)
-template <int KP, int VEC, int NCONV, int NE1G, int NCG>
-__global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_kernel(const __grid_constant__ ScoreTensorMaps tmaps, const __grid_constant__ StackArgs a) {
+template <int KP, int VEC, int NCONV, int NE1G, int NCG, int NE2G = 1>
+__global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) score_stack_kernel(const __grid_constant__ ScoreTensorMaps tmaps, const __grid_constant__ StackArgs a) {
     using S = StackSmem;
     using namespace umma;
     constexpr int J = KP <= 32 ? 64 / KP : 1;
     constexpr int K1S = J * KP / 16, K2S = KP / 16;
     constexpr int G = KP == 16 ? 8 : KP == 32 ? 4 : 2, T2 = G / 2;
-    constexpr uint32_t W_E1 = NCONV, W_E2 = NCONV + 8 * NE1G, W_PROD = W_E2 + 4, W_MMA = W_PROD + 1, W_MMA2 = W_PROD + 2, NT = (W_MMA2 + 1) * 32;
+    constexpr uint32_t W_E1 = NCONV, W_E2 = NCONV + 8 * NE1G, W_PROD = W_E2 + 4 * NE2G, W_MMA = W_PROD + 1, W_MMA2 = W_PROD + 2, NT = (W_MMA2 + 1) * 32;
     constexpr uint32_t NCT = NCONV * 32 / NCG;                            // threads that convert one tile
     constexpr uint32_t TM_A = 0, TM_D1 = 32;                              // TMEM columns: A | D1 x 2 | A2 x 2 (64 each) | D2 x NB2 (64 each)
     const uint32_t d1_stride = a.ncols <= 112 ? 112u : 128u;
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
             mbar_init(bx_full + b, NCONV / NCG); mbar_init(bx_free + b, 1);
             mbar_init(d1_full + b, 1); mbar_init(d1_free + b, 8);
             mbar_init(a2_full + b, 8); mbar_init(a2_free + b, 1);
-            mbar_init(d2_full + b, 1); mbar_init(d2_free + b, 4);
+            mbar_init(d2_full + b, 1); mbar_init(d2_free + b, 4);              // (4 warps of ONE epilogue-2 group read a tile)
         }
         mbar_init_fence();
     }
@@ -271,8 +275,11 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
                 TR_START();
                 if (!mbar_wait(a2_full + b, (m >> 1) & 1u)) { dead = true; break; }
                 TR_ADD(tr0);
-                const uint32_t b2 = nb2 == 2 ? b : 0u, use2 = nb2 == 2 ? (m >> 1) : m;      // D2 buffer and how often it has been filled
-                if (use2 >= 1 && !mbar_wait(d2_free + b2, (use2 - 1u) & 1u)) { dead = true; break; }
+                // D2 barriers go by tile parity (each epilogue-2 group, or the one group alternately, sees every phase of its own
+                // barrier); the buffer is b with two buffers, 0 with one - then the previous tile's reader must have let go of it
+                const uint32_t b2 = nb2 == 2 ? b : 0u;
+                if (nb2 == 2 ? (m >= 2 && !mbar_wait(d2_free + b, ((m >> 1) - 1u) & 1u))
+                             : (m >= 1 && !mbar_wait(d2_free + ((m - 1u) & 1u), ((m - 1u) >> 1) & 1u))) { dead = true; break; }
                 TR_ADD(tr1);
                 tc_fence_after_sync();
 #pragma unroll
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
                             mma_bf16_ts(d, (pass == 1 ? alo : ahi) + 8 * ks,
                                         desc_with_lo(desc2, (pass == 2 ? lo_c2_lo : lo_c2_hi) + ks * STEP2), a.idesc2, (pass | ks) != 0);
                 }
-                mma_commit(d2_full + b2);
+                mma_commit(d2_full + b);
                 mma_commit(a2_free + b);
                 TR_ADD(tr2);
             }
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
                 const uint32_t dst_hi = tmem + TM_A2 + b * 64 + t * KP + lane_s, dst_lo = dst_hi + KP / 2;
                 // all the map's columns are requested before the first wait (a TMEM load takes hundreds of cycles while the
                 // tensor core and the other epilogue warps use the same memory): one round trip per map instead of one per 16 columns
-                constexpr int NG = KP / 8, NB = NG > 4 ? 4 : NG;           // 8-column groups a map can have; groups per batch
+                constexpr int NG = KP / 8, NB = STACK_E1_BATCH < NG ? STACK_E1_BATCH : NG;   // 8-column groups a map can have; groups per batch
 #pragma unroll
                 for (int g0 = 0; g0 < NG; g0 += NB) {
                     uint32_t za[4 * NB], zb[4 * NB];
@@ -469,26 +476,22 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
         TR_FLUSH(24);
     } else if (warp < W_PROD) {
         // ================================================================ epilogue 2: D2 -> energies
-        const uint32_t q = warp & 3u, et = tid - W_E2 * 32;               // thread within the role
+        const uint32_t q = warp & 3u, eg2 = (warp - W_E2) >> 2, et = tid - (W_E2 + 4 * eg2) * 32;      // group, thread within it
         const uint32_t lane_q = (q * 32u) << 16;
         const uint32_t s = lane >> 4, r = lane & 15u;
         const uint32_t my_set = J == 4 ? q : J == 2 ? (q >> 1) : 0u;
         const uint32_t my_v = J == 4 ? r : J == 2 ? 16u * (q & 1u) + r : 16u * q + r;
-        uint32_t n = 0;
+        uint32_t n = eg2;
         int sg = 0;
         tr_me = tr_on && warp == W_E2 && lane == 0;
-        for (int tile = first; tile < a.num_tiles; tile += stride, ++n) {
+        for (int tile = first + (int)eg2 * stride; tile < a.num_tiles; tile += NE2G * stride, n += NE2G) {
             seg_of(tile, sg);
             const uint32_t C = static_cast<uint32_t>(a.seg.c_count[sg]), seg_maps = static_cast<uint32_t>(a.seg.n_maps[sg]);
             double* const accum = a.seg.accum[sg];
-            const uint32_t b2 = nb2 == 2 ? (n & 1u) : 0u, use2 = nb2 == 2 ? (n >> 1) : n;
+            const uint32_t pb = n & 1u, b2 = nb2 == 2 ? pb : 0u;           // barrier pair by tile parity, buffer
             TR_START();
-            {
-                bool ok = true;
-                ok = mbar_wait(d2_full + b2, use2 & 1u);
-                TR_ADD(tr0);
-                if (!ok) { dead = true; break; }
-            }
+            if (!mbar_wait(d2_full + pb, (n >> 1) & 1u)) { dead = true; break; }
+            TR_ADD(tr0);
             tc_fence_after_sync();
             const uint32_t d2 = tmem + TM_D2 + b2 * 64 + lane_q;
             const uint32_t m0 = static_cast<uint32_t>(tile - a.seg.tile0[sg]) * a.MT;      // first map of the tile within its segment
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
                 if (c0 + HALF >= TOT) {
                     tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(d2_free + b2);
+                    if (lane == 0) mbar_arrive(d2_free + pb);
                     TR_ADD(tr2);
                 }
 #pragma unroll
@@ -568,11 +571,11 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 7) * 32, 1) score_stack_ke
                 }
             } else {
                 // per-map energies asked for: the shares of a map are summed in a fixed order (bit-reproducible fp32 energy)
-                float* red_w = red + (n & 1u) * 32;
+                float* red_w = red + (NE2G == 2 ? eg2 : (n & 1u)) * 32;      // (one group: alternate; two: each its own)
                 if (r == 0)
 #pragma unroll
                     for (int t = 0; t < T2; ++t) red_w[q * 8 + 2 * t + s] = e[t];
-                named_bar_sync(1, 128);
+                named_bar_sync(1 + eg2, 128);
                 if (et < (uint32_t)a.MT) {
                     const uint32_t g = et / J, set = et % J;
                     float en;
