@@ -11,6 +11,9 @@ from .build import LIB_PATH
 PATH_AUTO, PATH_UMMA, PATH_SIMT, PATH_TMEM, PATH_LARGE, PATH_STACK, PATH_KRON = 0, 1, 2, 3, 4, 5, 6
 PATHS = {'auto': PATH_AUTO, 'umma': PATH_UMMA, 'simt': PATH_SIMT, 'tmem': PATH_TMEM, 'large': PATH_LARGE, 'stack': PATH_STACK, 'kron': PATH_KRON}
 
+OP_DCT2, OP_RANK, OP_RANK_SQ, OP_DCT3 = 0, 1, 2, 3
+OPS = {'dct2': OP_DCT2, 'rank': OP_RANK, 'rank_sq': OP_RANK_SQ, 'dct3': OP_DCT3}
+
 OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_DEVICE = 0, -1, -2, -3, -4
 
 _c = ctypes
@@ -26,6 +29,9 @@ _SIGNATURES = {
                                     _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                     _c.c_int, _c.c_void_p]),
     'dctp_score_accum_multi': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    'dctp_score_op': (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
+                                 _c.c_longlong, _c.c_longlong, _c.c_longlong,
+                                 _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     'dctp_finalize': (_c.c_int, [_c.c_void_p, _c.c_double, _c.c_void_p, _c.c_int, _c.c_void_p]),
     'dctp_topk_segmented': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                        _c.c_void_p, _c.c_void_p, _c.c_void_p]),

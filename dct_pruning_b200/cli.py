@@ -48,6 +48,9 @@ def build_parser():
                    help='score seeded random-init weights when --pretrain_dir does not exist (otherwise that is an error)')
     p.add_argument('--seed', type=int, default=0, help='seed of --random_init weights and of the data sampling')
     p.add_argument('--out_root', type=str, default='importance_score')
+    p.add_argument('--score_op', type=str, default='dct2', choices=('dct2', 'rank', 'rank_sq', 'dct3'),
+                   help="per-slice reduction: dct2 (utils/common.py:267, the default) or one of the lines the reference keeps commented out "
+                        "beside it: rank (HRank's matrix_rank, :268), rank_sq (the same through the unchanged cnt_score), dct3 (:269)")
     p.add_argument('--input_side', type=int, default=None, help='override the input resolution (e.g. 288 for DUTS crops)')
     return p
 

@@ -19,6 +19,7 @@
 #include "score_umma.cuh"
 #include "topk.cuh"
 #include "gather.cuh"
+#include "score_alt.cuh"
 
 namespace {
 
@@ -96,6 +97,9 @@ struct State {
     // scratch of dctp_score_host (grow-only)
     float* hx = nullptr; size_t hx_bytes = 0;
     double* hacc = nullptr; float* hout = nullptr; size_t hc = 0;
+    // scratch of dctp_score_op's DCT3 (grow-only): per-channel sums, per-(image, channel) energies
+    double* d3_part = nullptr; size_t d3_part_n = 0;
+    float* d3_energy = nullptr; size_t d3_energy_n = 0;
 } g;
 
 void note_kernel(const char* fmt, ...) {
@@ -692,6 +696,7 @@ int ensure_init() {
     CUDA_TRY(cudaFuncSetAttribute(score_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LargeSmem::TOTAL));
     CUDA_TRY(cudaFuncSetAttribute(score_simt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMALL_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(score_simt_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(rank_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RANK_SMEM_MAX));
     CUDA_TRY(cudaMalloc(&g.status, sizeof(int)));
     CUDA_TRY(cudaMemset(g.status, 0, sizeof(int)));
     g.ready = true;
@@ -1009,7 +1014,7 @@ int dctp_shutdown(void) {
     for (auto& kv : g.stack) { cudaFree(kv.second.a_img); cudaFree(kv.second.c2_hi); cudaFree(kv.second.c2_lo); cudaFree(kv.second.table); }
     for (auto& kv : g.kron) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
     g.umma.clear(); g.simt.clear(); g.tmem.clear(); g.large.clear(); g.stack.clear(); g.kron.clear();
-    cudaFree(g.status); cudaFree(g.hx); cudaFree(g.hacc); cudaFree(g.hout);
+    cudaFree(g.status); cudaFree(g.hx); cudaFree(g.hacc); cudaFree(g.hout); cudaFree(g.d3_part); cudaFree(g.d3_energy);
     g = State();
     return DCTP_OK;
 }
@@ -1173,6 +1178,91 @@ int dctp_score_accum_multi(const dctp_site* sites, int n_sites, int H, int W, vo
                                         sites[i].c_count, sites[i].accum, nullptr, nullptr, DCTP_PATH_AUTO, stream);
         if (rc) return rc;
     }
+    return DCTP_OK;
+}
+
+// ------------------------------------------------------------------ alternative scoring ops
+int dctp_score_op(int op, const float* x, int B, int H, int W, long long stride_b, long long stride_c, long long stride_h,
+                  int c_begin, int c_count, double* accum, float* values_out, void* stream) {
+    if (op == DCTP_OP_DCT2)
+        return dctp_score_accum(x, B, H, W, stride_b, stride_c, stride_h, c_begin, c_count, accum, values_out, nullptr, DCTP_PATH_AUTO, stream);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (op == DCTP_OP_RANK || op == DCTP_OP_RANK_SQ) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int rc = ensure_init();
+        if (rc) return rc;
+        if (B < 0 || H < 1 || W < 1 || c_begin < 0 || c_count < 0 || stride_h < W)
+            return fail(DCTP_E_INVALID, "dctp_score_op: B=%d H=%d W=%d c_begin=%d c_count=%d stride_h=%lld", B, H, W, c_begin, c_count, stride_h);
+        if (B == 0 || c_count == 0) return DCTP_OK;
+        if (!x || !accum) return fail(DCTP_E_INVALID, "dctp_score_op: null pointer");
+        RankArgs a;
+        a.x = x; a.stride_b = stride_b; a.stride_c = stride_c; a.stride_h = stride_h;
+        a.H = H; a.W = W; a.c_begin = c_begin; a.c_count = c_count;
+        a.n_maps = static_cast<long long>(B) * c_count;
+        a.accum = accum; a.out = values_out; a.squared = op == DCTP_OP_RANK_SQ;
+        a.by_cols = H > W;
+        a.n = H > W ? W : H; a.m = H > W ? H : W; a.ld = a.m | 1;
+        const size_t per_map = (static_cast<size_t>(a.n) * a.ld + a.n + 1) * sizeof(float);
+        if (a.m > RANK_MAX_LEN || per_map > static_cast<size_t>(RANK_SMEM_MAX))
+            return fail(DCTP_E_UNSUPPORTED, "the rank op holds a map in shared memory: longer side <= %d and %zu bytes <= %d (got %dx%d)",
+                        RANK_MAX_LEN, per_map, RANK_SMEM_MAX, H, W);
+        a.log2L = 0;
+        while ((RANK_EPT << a.log2L) < a.m) ++a.log2L;                  // lanes per pair: 8 elements each
+        const int L = 1 << a.log2L, np = (a.n + 1) / 2;
+        int threads = a.m <= 64 ? 256 : a.m <= 128 ? 512 : 1024;
+        const int workers = threads / L;
+        a.wpm = np < workers ? np : workers;
+        a.G = workers / a.wpm;
+        const int g_smem = static_cast<int>(static_cast<size_t>(64 * 1024) / per_map);       // keep several CTAs resident per SM
+        if (a.G > g_smem) a.G = g_smem < 1 ? 1 : g_smem;
+        if (a.G < 1) a.G = 1;
+        if (a.G > a.n_maps) a.G = static_cast<int>(a.n_maps);
+        threads = ((a.G * a.wpm * L + 31) / 32) * 32;
+        const size_t smem = per_map * a.G;
+        long long blocks = (a.n_maps + a.G - 1) / a.G;
+        const long long cap = static_cast<long long>(g.sm_count) * 32;
+        if (blocks > cap) blocks = cap;
+        rank_jacobi_kernel<<<static_cast<unsigned>(blocks), threads, smem, s>>>(a);
+        ++g.launches;
+        note_kernel("rank_jacobi_kernel (fp32 one-sided Jacobi SVD in shared memory, %d lanes per pair, %d maps per CTA)", L, a.G);
+        CUDA_TRY(cudaGetLastError());
+        return DCTP_OK;
+    }
+    if (op != DCTP_OP_DCT3) return fail(DCTP_E_INVALID, "dctp_score_op: unknown op %d", op);
+    // dct_3d energy of x[b, window] = sum over the window's channels of the 2-D energies (the channel-axis DCT is orthonormal)
+    if (B < 0 || c_count < 0) return fail(DCTP_E_INVALID, "dctp_score_op: B=%d c_count=%d", B, c_count);
+    if (B == 0 || c_count == 0) return DCTP_OK;
+    if (!accum) return fail(DCTP_E_INVALID, "dctp_score_op: null pointer");
+    double* part = nullptr;
+    float* energy = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int rc = ensure_init();
+        if (rc) return rc;
+        if (static_cast<size_t>(c_count) > g.d3_part_n) {
+            CUDA_TRY(cudaStreamSynchronize(s));                             // the old scratch may still be in use on this stream
+            cudaFree(g.d3_part); g.d3_part = nullptr; g.d3_part_n = 0;
+            CUDA_TRY(cudaMalloc(&g.d3_part, sizeof(double) * c_count));
+            g.d3_part_n = c_count;
+        }
+        const size_t ne = static_cast<size_t>(B) * c_count;
+        if (values_out && ne > g.d3_energy_n) {
+            CUDA_TRY(cudaStreamSynchronize(s));
+            cudaFree(g.d3_energy); g.d3_energy = nullptr; g.d3_energy_n = 0;
+            CUDA_TRY(cudaMalloc(&g.d3_energy, sizeof(float) * ne));
+            g.d3_energy_n = ne;
+        }
+        part = g.d3_part;
+        energy = values_out ? g.d3_energy : nullptr;
+        CUDA_TRY(cudaMemsetAsync(part, 0, sizeof(double) * c_count, s));
+    }
+    int rc = dctp_score_accum(x, B, H, W, stride_b, stride_c, stride_h, c_begin, c_count, part, energy, nullptr, DCTP_PATH_AUTO, stream);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (values_out) dct3_reduce_kernel<<<B, 256, 0, s>>>(energy, c_count, values_out, accum);
+    else sum_to_one_kernel<<<1, 256, 0, s>>>(part, c_count, accum);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
     return DCTP_OK;
 }
 

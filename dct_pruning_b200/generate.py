@@ -121,7 +121,7 @@ def inference(net, loader, limit, device, rank=0, world=1):
     return n
 
 
-def score_session(net, args, loader=None, path='auto'):
+def score_session(net, args, loader=None, path='auto', op=None):
     """Run the scoring pass (all hook sites live, `args.limit` batches, this rank's shard of every batch) and return the
     ScoreSession with its per-site energy sums still on the device, not yet reduced or finalised."""
     import torch.distributed as dist
@@ -135,7 +135,7 @@ def score_session(net, args, loader=None, path='auto'):
         side = getattr(args, 'input_side', None) or side
         loader = synthetic_batches(args.batch_size, side, args.limit,
                                    seed_base=getattr(args, 'seed_base', 1000), as_dict=(args.net == 'u2netp'))
-    session = ScoreSession(net, args.net, path=path)
+    session = ScoreSession(net, args.net, path=path, op=op or getattr(args, 'score_op', None) or 'dct2')
     if world > 1:                                       # same flat layout on every rank, also on one whose shards are all empty
         _, side0 = NET_INPUT[args.net]
         side0 = getattr(args, 'input_side', None) or side0
@@ -145,13 +145,15 @@ def score_session(net, args, loader=None, path='auto'):
     return session
 
 
-def imp_score(net, args, loader=None, out_root='importance_score', write=True, path='auto'):
+def imp_score(net, args, loader=None, out_root='importance_score', write=True, path='auto', op=None):
     """Score every hook site of `net` over `args.limit` batches and write the reference's files.
 
     args: namespace with .net, .limit, .batch_size (and optionally .seed_base).  Returns
-    {file_stem: float32 vector}.  The net must already live on a CUDA device."""
+    {file_stem: float32 vector}.  The net must already live on a CUDA device.  `op` (or args.score_op) selects the
+    per-slice reduction: 'dct2' (default, common.py:267) or one of the alternatives the reference keeps beside it - 'rank'
+    (HRank, :268), 'rank_sq' (:268 through the unchanged cnt_score), 'dct3' (:269, one value per site)."""
     import torch.distributed as dist
-    session = score_session(net, args, loader=loader, path=path)
+    session = score_session(net, args, loader=loader, path=path, op=op)
     files = session.finalize()
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0

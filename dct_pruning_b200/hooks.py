@@ -37,7 +37,12 @@ class ScoreSession:
     MAX_PENDING = 16
     HELD_BYTES = 8 << 30
 
-    def __init__(self, net, net_name, path='auto', capacity=1 << 18, sites=None, defer_bytes=None):
+    def __init__(self, net, net_name, path='auto', capacity=1 << 18, sites=None, defer_bytes=None, op='dct2'):
+        # op: the per-slice reduction - 'dct2' (common.py:267, the product), or one of the alternatives the reference keeps beside
+        # it: 'rank' (:268, HRank), 'rank_sq' (:268 followed by the unchanged cnt_score), 'dct3' (:269, one value per site)
+        if op not in _lib.OPS:
+            raise ValueError('unknown scoring op %r (one of %s)' % (op, ', '.join(_lib.OPS)))
+        self.op = op
         self.net = net
         self.net_name = net_name
         self.sites = list(hook_sites(net_name, net) if sites is None else sites)
@@ -50,6 +55,7 @@ class ScoreSession:
         self.handles = []
         self.lib = _lib.load()
         self._score_accum = self.lib.dctp_score_accum
+        self._score_op = self.lib.dctp_score_op
         self._plans = [None] * len(self.sites)
         self._planned = False                 # plan_layout() ran: slots exist for every site, in site order
         self.defer_bytes = self.DEFER_BYTES if defer_bytes is None else int(defer_bytes)
@@ -117,10 +123,18 @@ class ScoreSession:
                 c_begin, c_count = C - DENSENET_WINDOW, DENSENET_WINDOW
             else:
                 c_begin, c_count = 0, C
-            off = self._slot(idx, c_count, t.device)
+            off = self._slot(idx, 1 if self.op == 'dct3' else c_count, t.device)
             plan = self._plans[idx] = (C, c_begin, c_count, self.flat.data_ptr() + 8 * off)
         stream = torch.cuda.current_stream(t.device).cuda_stream
         c_begin, c_count = plan[1], plan[2]
+        if self.op != 'dct2':                 # the alternative ops: one launch per hook, same accumulator plumbing
+            with torch.cuda.device(t.device):
+                code = self._score_op(_lib.OPS[self.op], t.data_ptr(), B, H, W, sb, sc, sh, c_begin, c_count, plan[3], None, stream)
+            if code:
+                _lib.check(code)
+            self.images[idx] += B
+            self.launches += 1
+            return
         dense = sh == W and sc == H * W and (B == 1 or (c_count == C and sb == C * H * W))
         if (self.defer_bytes and dense and H == W and self.path == _lib.PATH_AUTO and 4 * B * c_count * H * W < self.defer_bytes
                 and (t.data_ptr() + 4 * c_begin * sc) % 16 == 0):
@@ -210,7 +224,7 @@ class ScoreSession:
                 continue
             C = shape[1]
             c_count = DENSENET_WINDOW if site.variant == VARIANT_LAST12 else C
-            self._slot(idx, c_count, example.device)
+            self._slot(idx, 1 if self.op == 'dct3' else c_count, example.device)
         self._planned = True
         return self
 
@@ -320,7 +334,8 @@ class ScoreSession:
                 continue
             vec = host_scores[slot[0]:slot[0] + slot[1]]
             for f in site.files:
-                files[f.stem] = np.array(vec if f.lo is None else vec[f.lo:f.hi], dtype=np.float32, copy=True)
+                whole = f.lo is None or self.op == 'dct3'        # dct3: one value per site, no per-branch slices
+                files[f.stem] = np.array(vec if whole else vec[f.lo:f.hi], dtype=np.float32, copy=True)
         return files
 
     def file_segments(self):
@@ -330,6 +345,6 @@ class ScoreSession:
             if slot is None:
                 continue
             for f in site.files:
-                lo, hi = (0, slot[1]) if f.lo is None else (f.lo, f.hi)
+                lo, hi = (0, slot[1]) if (f.lo is None or self.op == 'dct3') else (f.lo, f.hi)
                 segs.append((f.stem, slot[0] + lo, hi - lo))
         return segs

@@ -95,6 +95,25 @@ typedef struct dctp_site {
 } dctp_site;
 int dctp_score_accum_multi(const dctp_site* sites, int n_sites, int H, int W, void* stream);
 
+/* Alternative per-slice scoring ops behind the same accumulate / finalise / top-k plumbing: the two lines the reference keeps
+ * commented out beside the DCT in get_feature_hook and compares against in chart*.py.
+ *   DCTP_OP_DCT2     utils/common.py:267  dct_2d energy per (image, channel)             == dctp_score_accum(..., DCTP_PATH_AUTO)
+ *   DCTP_OP_RANK     utils/common.py:268  torch.matrix_rank(output[i,j,:,:]) (HRank): accum[j] += sum_b rank(x[b, c_begin + j]),
+ *                    rank = #{sigma > sigma_max * max(H, W) * eps_fp32} of the fp32 map (one-sided Jacobi SVD on the GPU)
+ *   DCTP_OP_RANK_SQ  the same line left in front of the unchanged cnt_score (:249-255, :271), which squares every entry:
+ *                    accum[j] += sum_b rank^2
+ *   DCTP_OP_DCT3     utils/common.py:269  dct_3d(output[i,:,:,:]) -> cnt_score: ONE value per image, accum[0] += sum_b energy of the
+ *                    3-D coefficient cube over channels [c_begin, c_begin + c_count) (accum has ONE entry for this op)
+ * values_out  optional fp32: per-(image, channel) value [B * c_count] for DCT2 / RANK / RANK_SQ, per-image energy [B] for DCT3.
+ * RANK / RANK_SQ hold a map in shared memory: longer side <= 256 and side <= 224 for square maps (DCTP_E_UNSUPPORTED beyond). */
+#define DCTP_OP_DCT2     0
+#define DCTP_OP_RANK     1
+#define DCTP_OP_RANK_SQ  2
+#define DCTP_OP_DCT3     3
+int dctp_score_op(int op, const float* x, int B, int H, int W,
+                  long long stride_b, long long stride_c, long long stride_h,
+                  int c_begin, int c_count, double* accum, float* values_out, void* stream);
+
 /* out[i] = (float)(accum[i] / n_images).  Replaces the running mean over images
  * (utils/common.py:275-277) and the fp32 vector np.save writes (:394). */
 int dctp_finalize(const double* accum, double n_images, float* out, int n, void* stream);

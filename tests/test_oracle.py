@@ -126,3 +126,40 @@ def test_running_mean_equals_sum_over_images():
         st.update(c * 3, 3)
     want = sum(c.double() * 3 for c in chunks) / 12
     np.testing.assert_allclose(st.feature_result.numpy(), want.numpy(), rtol=1e-6)
+
+
+# ------------------------------------------------------------------ alternative scoring ops
+def test_alt_oracle_dct3_matches_scipy_and_parseval():
+    """oracle dct_3d (the 1-D port along three axes) == scipy's 3-D dctn; its energy == sum of squares (orthonormal)."""
+    from scipy.fft import dctn
+    from oracle import alt_ops_port as ao, torch_dct_port as dct
+    x = torch.relu(torch.randn(2, 6, 9, 12, generator=torch.Generator().manual_seed(3)))
+    for b in range(2):
+        cube = dct.dct_3d(x[b], norm='ortho').numpy()
+        np.testing.assert_allclose(cube, dctn(x[b].numpy(), norm='ortho'), atol=2e-5)
+    e = ao.dct3_energy64(x.numpy())
+    np.testing.assert_allclose(e, (x.double() ** 2).sum((1, 2, 3)).numpy(), rtol=1e-12)
+    st = port.ScoreState()
+    ao.hook_dct3(st)(None, None, x)
+    assert st.feature_result.shape == (1,)
+    np.testing.assert_allclose(float(st.feature_result[0]), e.mean(), rtol=1e-5)
+
+
+def test_alt_oracle_rank_rule_matches_numpy():
+    """The oracle's rank (torch.linalg.matrix_rank, successor of the removed torch.matrix_rank) applies the rule of the reference's
+    line: S > S.max() * max(H, W) * eps.  numpy's matrix_rank states the same rule on LAPACK's singular values."""
+    from oracle import alt_ops_port as ao
+    g = torch.Generator().manual_seed(11)
+    cases = [torch.zeros(5, 5), torch.eye(7), torch.randn(9, 3, generator=g) @ torch.randn(3, 9, generator=g),
+             torch.relu(torch.randn(12, 12, generator=g) - 0.8), torch.randn(6, 10, generator=g)]
+    for m in cases:
+        s = np.linalg.svd(m.numpy(), compute_uv=False)
+        by_rule = int((s > s.max(initial=0) * max(m.shape) * np.finfo(np.float32).eps).sum())
+        assert ao.matrix_rank(m) == by_rule == int(np.linalg.matrix_rank(m.numpy()))
+    x = torch.stack(cases[:1] + [torch.eye(5)])[None]
+    st = port.ScoreState()
+    ao.hook_rank(st)(None, None, x)
+    assert st.feature_result.tolist() == [0.0, 5.0]
+    st = port.ScoreState()
+    ao.hook_rank(st, through_cnt_score=True)(None, None, x)
+    assert st.feature_result.tolist() == [0.0, 25.0]
