@@ -301,38 +301,45 @@ int get_stack_basis(int N, StackBasis& out) {
     return DCTP_OK;
 }
 
-// instantiations: variant v = (KP 16, VEC 4), (16, 2), (32, 4), (32, 2), (48, 4), (64, 4); configuration cfg = role layout
-//   cfg 0: 8 converter warps in two groups (alternate tiles), one epilogue-1 group, 23 warps
-//   cfg 1: the same with two epilogue-1 groups, 31 warps            cfg 2: 4 converter warps in one group, 19 warps
-//   cfg 3: 4 converter warps in two groups, two epilogue-1 and two epilogue-2 groups, 31 warps      cfg 4 (default): cfg 0 with two epilogue-2 groups, 27 warps
-// same box, cfg 0 / cfg 4: 56x56 3.73 / 3.73, 28x28 3.47 / 3.62, 14x14 3.19 / 3.25 TB/s; cfg 3 3.49 at 56x56
-// measured on B200, [256,C,N,N] 56x56 / 28x28 / 14x14, TB/s: cfg 0 3.85 / 3.67 / 3.26, cfg 1 3.78 / 3.57 / 3.12, cfg 2 3.59 / 3.31 / 2.89
-constexpr int STACK_CFGS = 5;
+// instantiations: variant v = (KP, VEC, Np / 8) - (16,4,2) (16,2,2) (32,4,3) (32,4,4) (32,2,3) (32,2,4) (48,4,5) (48,4,6) (64,4,7) (64,4,8);
+// configuration cfg = role layout:
+//   cfg 4 (default): 8 converter warps in two groups (alternate tiles), one epilogue-1 group, two epilogue-2 groups, 27 warps
+//   cfg 5: cfg 4 with register rebalancing (setmaxnreg; 28 warps, one TMEM round trip per tile in epilogue 1): measured slower
+//          (56x56 3.36 against 3.61 TB/s - the epilogue's arithmetic, not its TMEM latency, is what takes the time)
+//   cfg 6: cfg 4 with the cycle accounting of DCTP_S_TRACE compiled in (selected by the environment variable, never by default)
+// Round-2 layouts measured and retired (same box, 56x56 / 28x28 / 14x14 TB/s): one epilogue-2 group 3.73 / 3.47 / 3.19 (cfg 4: 3.73 /
+// 3.62 / 3.25), two epilogue-1 groups 3.78 / 3.57 / 3.12, 4 converter warps 3.59 / 3.31 / 2.89.
+constexpr int STACK_CFGS = 7, STACK_VARIANTS = 10;
 typedef void (*StackKernel)(const ScoreTensorMaps, const StackArgs);
-template <int NCONV, int NE1G, int NCG, int NE2G = 1>
+template <bool RB, bool TRACE>
 StackKernel stack_kernel_of(int v) {
     switch (v) {
-        case 0: return score_stack_kernel<16, 4, NCONV, NE1G, NCG, NE2G>;
-        case 1: return score_stack_kernel<16, 2, NCONV, NE1G, NCG, NE2G>;
-        case 2: return score_stack_kernel<32, 4, NCONV, NE1G, NCG, NE2G>;
-        case 3: return score_stack_kernel<32, 2, NCONV, NE1G, NCG, NE2G>;
-        case 4: return score_stack_kernel<48, 4, NCONV, NE1G, NCG, NE2G>;
-        default: return score_stack_kernel<64, 4, NCONV, NE1G, NCG, NE2G>;
+        case 0: return score_stack_kernel<16, 4, 8, 1, 2, 2, RB, 2, TRACE>;
+        case 1: return score_stack_kernel<16, 2, 8, 1, 2, 2, RB, 2, TRACE>;
+        case 2: return score_stack_kernel<32, 4, 8, 1, 2, 2, RB, 3, TRACE>;
+        case 3: return score_stack_kernel<32, 4, 8, 1, 2, 2, RB, 4, TRACE>;
+        case 4: return score_stack_kernel<32, 2, 8, 1, 2, 2, RB, 3, TRACE>;
+        case 5: return score_stack_kernel<32, 2, 8, 1, 2, 2, RB, 4, TRACE>;
+        case 6: return score_stack_kernel<48, 4, 8, 1, 2, 2, RB, 5, TRACE>;
+        case 7: return score_stack_kernel<48, 4, 8, 1, 2, 2, RB, 6, TRACE>;
+        case 8: return score_stack_kernel<64, 4, 8, 1, 2, 2, RB, 7, TRACE>;
+        default: return score_stack_kernel<64, 4, 8, 1, 2, 2, RB, 8, TRACE>;
     }
 }
 StackKernel stack_kernel_fn(int cfg, int v) {
     switch (cfg) {
-        case 1: return stack_kernel_of<8, 2, 2>(v);
-        case 2: return stack_kernel_of<4, 1, 1>(v);
-        case 3: return stack_kernel_of<4, 2, 2, 2>(v);
-        case 4: return stack_kernel_of<8, 1, 2, 2>(v);
-        default: return stack_kernel_of<8, 1, 2>(v);
+        case 5: return stack_kernel_of<true, false>(v);
+        case 6: return stack_kernel_of<false, true>(v);
+        default: return stack_kernel_of<false, false>(v);
     }
 }
 const void* stack_kernel_ptr(int cfg, int v) { return reinterpret_cast<const void*>(stack_kernel_fn(cfg, v)); }
-int stack_threads(int cfg) {
-    static const int warps[STACK_CFGS] = {8 + 8 + 4 + 3, 8 + 16 + 4 + 3, 4 + 8 + 4 + 3, 4 + 16 + 8 + 3, 8 + 8 + 8 + 3};
-    return warps[cfg] * 32;
+int stack_threads(int cfg) { return (cfg == 5 ? 28 : 27) * 32; }
+int stack_variant(int KP, int vec, int np8) {
+    if (KP == 16) return vec == 4 ? 0 : 1;
+    if (KP == 32) return (vec == 4 ? 2 : 4) + (np8 == 4 ? 1 : 0);
+    if (KP == 48) return np8 == 6 ? 7 : 6;
+    return np8 == 8 ? 9 : 8;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -407,9 +414,11 @@ int launch_stack(const SiteDesc* sites, int n, int N, float* energy_out, float* 
         CUDA_TRY(cudaMemset(trace_buf, 0, 64 * sizeof(long long)));
         a.trace = trace_buf;
     }
-    const int variant = KP == 16 ? (v4 ? 0 : 1) : KP == 32 ? (v4 ? 2 : 3) : KP == 48 ? 4 : 5;
-    CUDA_TRY(launch_score_tma(stack_kernel_fn(g.stack_cfg, variant), grid, stack_threads(g.stack_cfg), smem, stream, maps, a));
-    note_kernel("score_stack_kernel<KP=%d,VEC=%d,cfg%d> (tcgen05, stacked hi/lo basis in TMEM, TMA tile ring, warp specialised)", KP, basis.vec, g.stack_cfg);
+    const int variant = stack_variant(KP, v4 ? 4 : 2, a.Np / 8);
+    // per-map energies, coefficients and the cycle trace live in the debug instantiation (cfg 6) only
+    const int cfg = (a.energy_out || a.dump || tracing) ? 6 : g.stack_cfg;
+    CUDA_TRY(launch_score_tma(stack_kernel_fn(cfg, variant), grid, stack_threads(cfg), smem, stream, maps, a));
+    note_kernel("score_stack_kernel<KP=%d,VEC=%d,cfg%d> (tcgen05, stacked hi/lo basis in TMEM, TMA tile ring, warp specialised)", KP, basis.vec, cfg);
     if (tracing) {
         long long h[64];
         CUDA_TRY(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
@@ -420,6 +429,9 @@ int launch_stack(const SiteDesc* sites, int n, int N, float* energy_out, float* 
                         "epi2: wait D2 %.0f, TMEM loads %.0f, sums+shuffles %.0f, atomics %.0f\n",
                 N, g.stack_cfg, h[14], h[0] / nt, h[16] / nt, h[17] / nt, h[18] / nt, h[19] / nt, h[8] / nt, h[9] / nt, h[10] / nt, h[40] / nt,
                 h[41] / nt, h[42] / nt, h[24] / nt, h[25] / nt, h[26] / nt, h[32] / nt, h[34] / nt, h[35] / nt, h[33] / nt);
+        fprintf(stderr, "[dctp trace] epi1 work split: TMEM loads %.0f, convert + store issue %.0f, store wait + arrive %.0f\n", h[27] / nt, h[28] / nt, h[26] / nt);
+        fprintf(stderr, "[dctp trace] tile loop of CTA 0: %lld SM cycles in %lld ns = %.0f MHz, %.0f cycles per tile\n", h[50], h[51],
+                h[51] > 0 ? 1e3 * double(h[50]) / double(h[51]) : 0.0, double(h[50]) / nt);
     }
     g.launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -665,8 +677,8 @@ int ensure_init() {
         }
     }
     {
-        for (int cfg = 0; cfg < STACK_CFGS; ++cfg)
-            for (int v = 0; v < 6; ++v) {
+        for (int cfg = 4; cfg < STACK_CFGS; ++cfg)
+            for (int v = 0; v < STACK_VARIANTS; ++v) {
                 const void* fn = stack_kernel_ptr(cfg, v);
                 CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(StackSmem::TOTAL)));
                 CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -684,7 +696,7 @@ int ensure_init() {
         if (!g.encode_tiled) return fail(DCTP_E_CUDA, "the driver does not export cuTensorMapEncodeTiled");
     }
     if (const char* e = std::getenv("DCTP_KRON")) g.kron_on = std::atoi(e) != 0;
-    if (const char* e = std::getenv("DCTP_STACK_CFG")) { g.stack_cfg = std::atoi(e); if (g.stack_cfg < 0 || g.stack_cfg >= STACK_CFGS) g.stack_cfg = 4; }
+    if (const char* e = std::getenv("DCTP_STACK_CFG")) { g.stack_cfg = std::atoi(e); if (g.stack_cfg < 4 || g.stack_cfg >= STACK_CFGS) g.stack_cfg = 4; }
     if (const char* e = std::getenv("DCTP_STACK")) g.stack_on = std::atoi(e) != 0;
     if (const char* e = std::getenv("DCTP_STACK_MIN_MB")) g.stack_min_bytes = static_cast<long long>(std::atoi(e)) << 20;
     if (const char* e = std::getenv("DCTP_TP")) g.t_prod = std::atoi(e) != 0;

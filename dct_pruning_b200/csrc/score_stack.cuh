@@ -99,14 +99,21 @@ struct StackSmem {
 // Every warp polls the mbarriers it depends on itself.  (Measured and dropped: one polling warp per role releasing its siblings
 // through a named barrier - the polls cost issue slots, the sleep behind mbarrier.try_wait being woken by any barrier event of
 // the CTA, but the extra hop costs more: 56x56 3.17 against 3.49 TB/s.)
-template <int KP, int VEC, int NCONV, int NE1G, int NCG, int NE2G = 1>
-__global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) score_stack_kernel(const __grid_constant__ ScoreTensorMaps tmaps, const __grid_constant__ StackArgs a) {
+// RB: register rebalancing (setmaxnreg).  The roles need very different register counts - a converter thread ~40, an epilogue-1 thread
+// 64 for ONE TMEM round trip per tile instead of two (its busy time per tile is what sets the tile period: 1040 of ~1400 cycles, two
+// thirds of it waiting for tcgen05.ld) - but a CTA of 27 warps gets 72 each.  With RB the control warps are padded to a full warpgroup
+// (28 warps), converters, epilogue 2 and control give registers back and the epilogue-1 warpgroups take them (120).
+// NP8: Np / 8 as a compile-time constant (0: read it from the arguments) - epilogue 1's column loops lose their branches.
+// TRACE: the debug instantiation - the cycle accounting of DCTP_S_TRACE, the per-map energies (energy_out) and the coefficient dump
+// (coeff_out); the production instantiations carry none of that code (the host routes launches that ask for any of it here).
+template <int KP, int VEC, int NCONV, int NE1G, int NCG, int NE2G = 1, bool RB = false, int NP8 = 0, bool TRACE = false>
+__global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) * 32, 1) score_stack_kernel(const __grid_constant__ ScoreTensorMaps tmaps, const __grid_constant__ StackArgs a) {
     using S = StackSmem;
     using namespace umma;
     constexpr int J = KP <= 32 ? 64 / KP : 1;
     constexpr int K1S = J * KP / 16, K2S = KP / 16;
     constexpr int G = KP == 16 ? 8 : KP == 32 ? 4 : 2, T2 = G / 2;
-    constexpr uint32_t W_E1 = NCONV, W_E2 = NCONV + 8 * NE1G, W_PROD = W_E2 + 4 * NE2G, W_MMA = W_PROD + 1, W_MMA2 = W_PROD + 2, NT = (W_MMA2 + 1) * 32;
+    constexpr uint32_t W_E1 = NCONV, W_E2 = NCONV + 8 * NE1G, W_PROD = W_E2 + 4 * NE2G, W_MMA = W_PROD + 1, W_MMA2 = W_PROD + 2, NT = (W_MMA2 + (RB ? 2 : 1)) * 32;
     constexpr uint32_t NCT = NCONV * 32 / NCG;                            // threads that convert one tile
     constexpr uint32_t TM_A = 0, TM_D1 = 32;                              // TMEM columns: A | D1 x 2 | A2 x 2 (64 each) | D2 x NB2 (64 each)
     const uint32_t d1_stride = a.ncols <= 112 ? 112u : 128u;
@@ -116,7 +123,8 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
     constexpr uint32_t STEP2 = (2 * S::LBO2) >> 4;
 
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // (the warp index comes out of a shuffle so that the compiler knows it is warp-uniform: role addresses stay in uniform registers)
+    const uint32_t tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     uint8_t* stg = smem;
     uint8_t* bx = smem + S::OFF_BX;                                       // [buffer][hi | lo]
     uint8_t* c2 = smem + S::OFF_C2;
@@ -192,6 +200,11 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
     }
     grid_dependency_wait();                                               // the activation is complete
 
+    long long tr_c0 = 0, tr_g0 = 0;
+    if (TRACE && a.trace != nullptr && blockIdx.x == 0 && tid == 0) {
+        tr_c0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_g0));
+    }
     const int first = blockIdx.x, stride = gridDim.x;
     const uint32_t tile_bytes = static_cast<uint32_t>(a.tile_rows) * 128u;
     bool dead = false;
@@ -204,15 +217,18 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
         return tile == a.seg.tile0[sg + 1] - 1 && (a.seg.total_elems[sg] & 31) != 0;
     };
     // bring-up trace: one thread per role accumulates cycles in registers and writes them when its loop ends
-    const bool tr_on = a.trace != nullptr && blockIdx.x == 0;
+    const bool tr_on = TRACE && a.trace != nullptr && blockIdx.x == 0;
     bool tr_me = false;
     long long tr_mark = 0, tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0, tr5 = 0;
 #define TR_START() do { if (tr_me) tr_mark = clock64(); } while (0)
 #define TR_ADD(acc) do { if (tr_me) { const long long now_ = clock64(); (acc) += now_ - tr_mark; tr_mark = now_; } } while (0)
 #define TR_FLUSH(base) do { if (tr_me) { a.trace[(base)] = tr0; a.trace[(base) + 1] = tr1; a.trace[(base) + 2] = tr2; a.trace[(base) + 3] = tr3; \
                                          a.trace[(base) + 4] = tr4; a.trace[(base) + 5] = tr5; } } while (0)
+    // (RB: the register hand-over sits at the top of every role's branch, so that the branch is compiled against its own count;
+    //  whole warpgroups - every role is a multiple of 4 warps with RB, the three control warps and a spare one share the last)
     if (warp == W_PROD) {
         // ================================================================ TMA producer
+        if constexpr (RB) reg_dealloc<24>();
         if (elect_one()) {
             tr_me = tr_on;
             uint32_t it = 0;
@@ -233,6 +249,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
         __syncwarp();
     } else if (warp == W_MMA) {
         // ================================================================ MMA issuer, stage 1: D1 = A * Bx^T (Bx_hi, then Bx_lo)
+        if constexpr (RB) reg_dealloc<24>();
         if (elect_one()) {
             tr_me = tr_on;
             const uint64_t desc = make_smem_desc(0, a.lbo1, 128, SWIZZLE_NONE);
@@ -259,11 +276,12 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
                 TR_ADD(tr2);
             }
             TR_FLUSH(8);
-            if (tr_me) a.trace[14] = n;
+            if (TRACE && tr_me) a.trace[14] = n;
         }
         __syncwarp();
     } else if (warp == W_MMA2) {
         // ================================================================ MMA issuer, stage 2: D2 = A2 * C^T (hi*hi + lo*hi + hi*lo)
+        if constexpr (RB) reg_dealloc<24>();
         if (elect_one()) {
             tr_me = tr_on;
             const uint64_t desc2 = make_smem_desc(0, S::LBO2, 128, SWIZZLE_NONE);
@@ -302,6 +320,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
         __syncwarp();
     } else if (warp < W_E1) {
         // ================================================================ converters: fp32 tile -> bf16 hi/lo -> Bx
+        if constexpr (RB) reg_dealloc<56>();
         const uint32_t cg = warp / (NCONV / NCG), ctid = tid - cg * NCT;     // converter group, thread within it
         uint32_t n = 0, it = 0;                                            // the CTA's tile number / its TMA sequence number
         int sg = 0;
@@ -327,8 +346,8 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
             uint8_t* lo = hi + S::BX_HALF;
             auto emit = [&](uint32_t o, const float4 v) {                  // o: table entry of the vector
                 uint32_t h0, l0, h1, l1;
-                split2(v.x, v.y, h0, l0);
-                split2(v.z, v.w, h1, l1);
+                split2_packed(pack2(__float_as_uint(v.x), __float_as_uint(v.y)), h0, l0);
+                split2_packed(pack2(__float_as_uint(v.z), __float_as_uint(v.w)), h1, l1);
                 if constexpr (VEC == 4) {
                     *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
                     *reinterpret_cast<uint2*>(lo + o) = make_uint2(l0, l1);
@@ -395,9 +414,10 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
         TR_FLUSH(16);
     } else if (warp < W_E2) {
         // ================================================================ epilogue 1: D1 -> y = za + zb -> bf16 hi/lo -> A2
+        if constexpr (RB) reg_alloc<104>();
         const uint32_t q = warp & 3u, s = ((warp - W_E1) >> 2) & 1u, eg = (warp - W_E1) >> 3;
         const uint32_t lane_q = (q * 32u) << 16, lane_s = (q * 32u + s * 16u) << 16;
-        const int np8 = a.Np >> 3;
+        const int np8 = NP8 ? NP8 : (a.Np >> 3);
         tr_me = tr_on && warp == W_E1 && lane == 0;
         auto convert16 = [&](const uint32_t (&za)[8], const uint32_t (&zb)[8], uint32_t dst_hi, uint32_t dst_lo) {
             uint32_t h[4], l[4];
@@ -421,6 +441,50 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
                 if (!ok) { dead = true; break; }
             }
             tc_fence_after_sync();
+            if constexpr (RB) {
+                // every column of D1 this warp needs (T2 maps x Np columns, both lane halves: 64 registers) is requested before the one
+                // wait: a TMEM load takes 200-350 cycles while the tensor core and the other warps use the same memory
+                constexpr int NG = KP / 8;
+                uint32_t za[T2][4 * NG], zb[T2][4 * NG];
+#pragma unroll
+                for (int t = 0; t < T2; ++t) {
+                    const uint32_t src_a = d1 + lane_q + (2 * t + s) * a.Np, src_b = src_a + (16u << 16);
+#pragma unroll
+                    for (int c8 = 0; c8 < NG; c8 += 2) {
+                        if (c8 + 2 <= np8) {
+                            tmem_ld_frag16(src_a + c8 * 8, reinterpret_cast<uint32_t (&)[8]>(za[t][4 * c8]));
+                            tmem_ld_frag16(src_b + c8 * 8, reinterpret_cast<uint32_t (&)[8]>(zb[t][4 * c8]));
+                        } else if (c8 < np8) {
+                            tmem_ld_frag8(src_a + c8 * 8, reinterpret_cast<uint32_t (&)[4]>(za[t][4 * c8]));
+                            tmem_ld_frag8(src_b + c8 * 8, reinterpret_cast<uint32_t (&)[4]>(zb[t][4 * c8]));
+                        }
+                    }
+                }
+                tmem_ld_wait();
+                TR_ADD(tr3);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d1_free + b);
+#pragma unroll
+                for (int t = 0; t < T2; ++t) {
+                    const uint32_t dst_hi = tmem + TM_A2 + b * 64 + t * KP + lane_s, dst_lo = dst_hi + KP / 2;
+#pragma unroll
+                    for (int c8 = 0; c8 < NG; c8 += 2) {
+                        if (c8 + 2 <= np8) {
+                            convert16(reinterpret_cast<const uint32_t (&)[8]>(za[t][4 * c8]), reinterpret_cast<const uint32_t (&)[8]>(zb[t][4 * c8]),
+                                      dst_hi + c8 * 4, dst_lo + c8 * 4);
+                        } else if (c8 < np8) {
+                            uint32_t h[2], l[2];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                split2_packed(add2_packed(pack2(za[t][4 * c8 + 2 * i], za[t][4 * c8 + 2 * i + 1]),
+                                                          pack2(zb[t][4 * c8 + 2 * i], zb[t][4 * c8 + 2 * i + 1])), h[i], l[i]);
+                            tmem_st_frag4(dst_hi + c8 * 4, h[0], h[1]);
+                            tmem_st_frag4(dst_lo + c8 * 4, l[0], l[1]);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int t = 0; t < T2; ++t) {
                 const uint32_t col0 = (2 * t + s) * a.Np;                 // this warp's map of A2 tile t
@@ -467,6 +531,8 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
                     }
                 }
             }
+            }
+            TR_ADD(tr4);
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
@@ -476,13 +542,15 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
         TR_FLUSH(24);
     } else if (warp < W_PROD) {
         // ================================================================ epilogue 2: D2 -> energies
+        if constexpr (RB) reg_dealloc<64>();
         const uint32_t q = warp & 3u, eg2 = (warp - W_E2) >> 2, et = tid - (W_E2 + 4 * eg2) * 32;      // group, thread within it
         const uint32_t lane_q = (q * 32u) << 16;
         const uint32_t s = lane >> 4, r = lane & 15u;
         const uint32_t my_set = J == 4 ? q : J == 2 ? (q >> 1) : 0u;
         const uint32_t my_v = J == 4 ? r : J == 2 ? 16u * (q & 1u) + r : 16u * q + r;
         uint32_t n = eg2;
-        int sg = 0;
+        int sg = 0, chan_sg = -1;
+        uint32_t chan0 = 0, chan_step = 0;
         tr_me = tr_on && warp == W_E2 && lane == 0;
         for (int tile = first + (int)eg2 * stride; tile < a.num_tiles; tile += NE2G * stride, n += NE2G) {
             seg_of(tile, sg);
@@ -495,7 +563,15 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
             tc_fence_after_sync();
             const uint32_t d2 = tmem + TM_D2 + b2 * 64 + lane_q;
             const uint32_t m0 = static_cast<uint32_t>(tile - a.seg.tile0[sg]) * a.MT;      // first map of the tile within its segment
-            const uint32_t chan0 = m0 % C;                                 // (n_maps < 2^30: 32-bit arithmetic)
+            // channel of the tile's first map: m0 mod C, kept up incrementally (one division per segment, not per tile)
+            if (sg != chan_sg) {
+                chan_sg = sg;
+                chan0 = m0 % C;                                            // (n_maps < 2^30: 32-bit arithmetic)
+                chan_step = (static_cast<uint32_t>(NE2G * stride) * static_cast<uint32_t>(a.MT)) % C;
+            } else {
+                chan0 += chan_step;
+                if (chan0 >= C) chan0 -= C;
+            }
             float e[T2];
             // the lane's T2 * KP (64 or 48) coefficients in two round trips of at most 32 registers; D2 is handed back as soon
             // as the second one has landed
@@ -530,7 +606,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
                         if (T2 == 4) part[t] += p;
                         else if (T2 == 2) part[t] += p;
                         else part[0] += p;
-                        if (a.dump != nullptr) {
+                        if (TRACE && a.dump != nullptr) {
                             const uint32_t m = m0 + (2 * t + s) * J + my_set;
                             const int u0 = (c0 + c) - t * KP;
                             if (m < seg_maps && my_v < (uint32_t)a.N)
@@ -551,7 +627,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
                 e[t] = v;                                                  // lanes of one half: the warp's share of map (2t + s, my_set)
             }
             TR_ADD(tr3);
-            if (a.energy_out == nullptr) {
+            if (!TRACE || a.energy_out == nullptr) {
                 // production: each warp adds its fp64 share of a map straight into the channel sum (J = 1: four shares per map).
                 // The warp's 2 * T2 shares are gathered into its first lanes so that they leave in ONE atomic instruction
                 // (lane l: A2 tile t = l / 2, row slot s = l % 2; the share sits in lane 16 s).
@@ -594,6 +670,8 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
             TR_ADD(tr1);
         }
         TR_FLUSH(32);
+    } else if constexpr (RB) {
+        reg_dealloc<24>();                                                 // the spare warp of the control warpgroup
     }
 #undef TR_START
 #undef TR_ADD
@@ -605,6 +683,12 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (TRACE && a.trace != nullptr && blockIdx.x == 0 && tid == 0) {    // tile loop of CTA 0 in SM cycles and in nanoseconds: the clock it ran at
+        long long g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        a.trace[50] = clock64() - tr_c0;
+        a.trace[51] = g1 - tr_g0;
+    }
     if (warp == W_MMA) tmem_dealloc<512>(tmem);
 }
 

@@ -58,6 +58,9 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     for (;;) {
 #pragma unroll 1
         for (int spin = 0; spin < 16; ++spin) {
+#if defined(DCTP_POLL_NS) && DCTP_POLL_NS > 0
+            __nanosleep(DCTP_POLL_NS);
+#endif
             if (mbar_try_wait(bar, parity)) return true;
         }
         if (global_ns() - t0 > 2000000000ull) return false;
@@ -108,6 +111,15 @@ __device__ __forceinline__ void fence_async_smem() {
 }
 
 // one lane of a converged warp (the compiler keeps the body on the uniform datapath)
+// Register rebalancing between the warpgroups of a warp-specialised CTA: every warp of a warpgroup (4 consecutive warps) executes it.
+template <uint32_t REGS>
+__device__ __forceinline__ void reg_alloc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+template <uint32_t REGS>
+__device__ __forceinline__ void reg_dealloc() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
