@@ -79,7 +79,7 @@ struct State {
     std::map<int, StackBasis> stack;                   // N
     std::map<int, KronBasis> kron;                     // N
     bool kron_on = true;                               // AUTO routes dense sides <= 8 to the Kronecker kernel (DCTP_KRON=0: round-1 kernels)
-    int stack_cfg = 4;                                 // role layout of the stacked-basis kernel (DCTP_STACK_CFG, see stack_kernel_fn)
+    int stack_cfg = 0;                                 // role layout of the stacked-basis kernel (DCTP_STACK_CFG, see stack_kernel_fn; 0: per side)
     bool stack_on = true;                              // AUTO routes dense even sides to the stacked-basis kernel (DCTP_STACK=0: round-1 kernels)
     long long stack_min_bytes = 0;                     // ... for launches of at least this many bytes (DCTP_STACK_MIN_MB)
     void* encode_tiled = nullptr;                      // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link dependency)
@@ -302,39 +302,42 @@ int get_stack_basis(int N, StackBasis& out) {
 }
 
 // instantiations: variant v = (KP, VEC, Np / 8) - (16,4,2) (16,2,2) (32,4,3) (32,4,4) (32,2,3) (32,2,4) (48,4,5) (48,4,6) (64,4,7) (64,4,8);
-// configuration cfg = role layout:
-//   cfg 4 (default): 8 converter warps in two groups (alternate tiles), one epilogue-1 group, two epilogue-2 groups, 27 warps
-//   cfg 5: cfg 4 with register rebalancing (setmaxnreg; 28 warps, one TMEM round trip per tile in epilogue 1): measured slower
-//          (56x56 3.36 against 3.61 TB/s - the epilogue's arithmetic, not its TMEM latency, is what takes the time)
-//   cfg 6: cfg 4 with the cycle accounting of DCTP_S_TRACE compiled in (selected by the environment variable, never by default)
-// Round-2 layouts measured and retired (same box, 56x56 / 28x28 / 14x14 TB/s): one epilogue-2 group 3.73 / 3.47 / 3.19 (cfg 4: 3.73 /
-// 3.62 / 3.25), two epilogue-1 groups 3.78 / 3.57 / 3.12, 4 converter warps 3.59 / 3.31 / 2.89.
-constexpr int STACK_CFGS = 7, STACK_VARIANTS = 10;
+// configuration cfg = role layout (one epilogue-1 group of 8 warps, two epilogue-2 groups of 4, producer, two issuers):
+//   cfg 4: 8 converter warps in two groups (alternate tiles), 27 warps        cfg 7: 12 converter warps (two groups of 6), 31 warps
+//   cfg 6: cfg 4 with the debug outputs compiled in (DCTP_S_TRACE cycle accounting, per-map energies, coefficient dump); the host
+//          routes launches that ask for any of them here, production launches never
+// AUTO (cfg 0): cfg 7 for sides above 32 (56x56: 4.12 against 4.03 TB/s), cfg 4 below (no difference there, fewer registers taken).
+// Layouts measured and retired in round 2 (same box, 56x56 / 28x28 / 14x14 TB/s, before the instruction diet): one epilogue-2 group
+// 3.73 / 3.47 / 3.19 (two: 3.73 / 3.62 / 3.25), two epilogue-1 groups 3.78 / 3.57 / 3.12, 4 converter warps 3.59 / 3.31 / 2.89;
+// after it: register rebalancing (setmaxnreg: converters 56, epilogue 1 104 registers and ONE TMEM round trip per tile) 3.36 against
+// 3.61 at 56x56; converters reading global memory directly behind an L2 bulk prefetch instead of the TMA-staged copy 3.46 against 4.07.
+constexpr int STACK_CFGS = 8, STACK_VARIANTS = 10;
 typedef void (*StackKernel)(const ScoreTensorMaps, const StackArgs);
-template <bool RB, bool TRACE>
+template <bool TRACE, int NCONV>
 StackKernel stack_kernel_of(int v) {
     switch (v) {
-        case 0: return score_stack_kernel<16, 4, 8, 1, 2, 2, RB, 2, TRACE>;
-        case 1: return score_stack_kernel<16, 2, 8, 1, 2, 2, RB, 2, TRACE>;
-        case 2: return score_stack_kernel<32, 4, 8, 1, 2, 2, RB, 3, TRACE>;
-        case 3: return score_stack_kernel<32, 4, 8, 1, 2, 2, RB, 4, TRACE>;
-        case 4: return score_stack_kernel<32, 2, 8, 1, 2, 2, RB, 3, TRACE>;
-        case 5: return score_stack_kernel<32, 2, 8, 1, 2, 2, RB, 4, TRACE>;
-        case 6: return score_stack_kernel<48, 4, 8, 1, 2, 2, RB, 5, TRACE>;
-        case 7: return score_stack_kernel<48, 4, 8, 1, 2, 2, RB, 6, TRACE>;
-        case 8: return score_stack_kernel<64, 4, 8, 1, 2, 2, RB, 7, TRACE>;
-        default: return score_stack_kernel<64, 4, 8, 1, 2, 2, RB, 8, TRACE>;
+        case 0: return score_stack_kernel<16, 4, NCONV, 1, 2, 2, 2, TRACE>;
+        case 1: return score_stack_kernel<16, 2, NCONV, 1, 2, 2, 2, TRACE>;
+        case 2: return score_stack_kernel<32, 4, NCONV, 1, 2, 2, 3, TRACE>;
+        case 3: return score_stack_kernel<32, 4, NCONV, 1, 2, 2, 4, TRACE>;
+        case 4: return score_stack_kernel<32, 2, NCONV, 1, 2, 2, 3, TRACE>;
+        case 5: return score_stack_kernel<32, 2, NCONV, 1, 2, 2, 4, TRACE>;
+        case 6: return score_stack_kernel<48, 4, NCONV, 1, 2, 2, 5, TRACE>;
+        case 7: return score_stack_kernel<48, 4, NCONV, 1, 2, 2, 6, TRACE>;
+        case 8: return score_stack_kernel<64, 4, NCONV, 1, 2, 2, 7, TRACE>;
+        default: return score_stack_kernel<64, 4, NCONV, 1, 2, 2, 8, TRACE>;
     }
 }
+bool stack_cfg_valid(int cfg) { return cfg == 4 || cfg == 6 || cfg == 7; }
 StackKernel stack_kernel_fn(int cfg, int v) {
     switch (cfg) {
-        case 5: return stack_kernel_of<true, false>(v);
-        case 6: return stack_kernel_of<false, true>(v);
-        default: return stack_kernel_of<false, false>(v);
+        case 6: return stack_kernel_of<true, 8>(v);
+        case 7: return stack_kernel_of<false, 12>(v);
+        default: return stack_kernel_of<false, 8>(v);
     }
 }
 const void* stack_kernel_ptr(int cfg, int v) { return reinterpret_cast<const void*>(stack_kernel_fn(cfg, v)); }
-int stack_threads(int cfg) { return (cfg == 5 ? 28 : 27) * 32; }
+int stack_threads(int cfg) { return (cfg == 7 ? 31 : 27) * 32; }
 int stack_variant(int KP, int vec, int np8) {
     if (KP == 16) return vec == 4 ? 0 : 1;
     if (KP == 32) return (vec == 4 ? 2 : 4) + (np8 == 4 ? 1 : 0);
@@ -416,7 +419,7 @@ int launch_stack(const SiteDesc* sites, int n, int N, float* energy_out, float* 
     }
     const int variant = stack_variant(KP, v4 ? 4 : 2, a.Np / 8);
     // per-map energies, coefficients and the cycle trace live in the debug instantiation (cfg 6) only
-    const int cfg = (a.energy_out || a.dump || tracing) ? 6 : g.stack_cfg;
+    const int cfg = (a.energy_out || a.dump || tracing) ? 6 : g.stack_cfg ? g.stack_cfg : (KP > 32 ? 7 : 4);
     CUDA_TRY(launch_score_tma(stack_kernel_fn(cfg, variant), grid, stack_threads(cfg), smem, stream, maps, a));
     note_kernel("score_stack_kernel<KP=%d,VEC=%d,cfg%d> (tcgen05, stacked hi/lo basis in TMEM, TMA tile ring, warp specialised)", KP, basis.vec, cfg);
     if (tracing) {
@@ -427,9 +430,8 @@ int launch_stack(const SiteDesc* sites, int n, int N, float* energy_out, float* 
                         "wait TMA %.0f, convert %.0f, fence+arrive %.0f | issuer 1: wait Bx %.0f, wait D1 free %.0f, issue %.0f | issuer 2: wait A2 %.0f, "
                         "wait D2 free %.0f, issue %.0f | epi1 (first group, per tile of the CTA): wait D1 %.0f, wait A2 free %.0f, work %.0f | "
                         "epi2: wait D2 %.0f, TMEM loads %.0f, sums+shuffles %.0f, atomics %.0f\n",
-                N, g.stack_cfg, h[14], h[0] / nt, h[16] / nt, h[17] / nt, h[18] / nt, h[19] / nt, h[8] / nt, h[9] / nt, h[10] / nt, h[40] / nt,
+                N, cfg, h[14], h[0] / nt, h[16] / nt, h[17] / nt, h[18] / nt, h[19] / nt, h[8] / nt, h[9] / nt, h[10] / nt, h[40] / nt,
                 h[41] / nt, h[42] / nt, h[24] / nt, h[25] / nt, h[26] / nt, h[32] / nt, h[34] / nt, h[35] / nt, h[33] / nt);
-        fprintf(stderr, "[dctp trace] epi1 work split: TMEM loads %.0f, convert + store issue %.0f, store wait + arrive %.0f\n", h[27] / nt, h[28] / nt, h[26] / nt);
         fprintf(stderr, "[dctp trace] tile loop of CTA 0: %lld SM cycles in %lld ns = %.0f MHz, %.0f cycles per tile\n", h[50], h[51],
                 h[51] > 0 ? 1e3 * double(h[50]) / double(h[51]) : 0.0, double(h[50]) / nt);
     }
@@ -678,7 +680,7 @@ int ensure_init() {
     }
     {
         for (int cfg = 4; cfg < STACK_CFGS; ++cfg)
-            for (int v = 0; v < STACK_VARIANTS; ++v) {
+            for (int v = 0; stack_cfg_valid(cfg) && v < STACK_VARIANTS; ++v) {
                 const void* fn = stack_kernel_ptr(cfg, v);
                 CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(StackSmem::TOTAL)));
                 CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -696,7 +698,7 @@ int ensure_init() {
         if (!g.encode_tiled) return fail(DCTP_E_CUDA, "the driver does not export cuTensorMapEncodeTiled");
     }
     if (const char* e = std::getenv("DCTP_KRON")) g.kron_on = std::atoi(e) != 0;
-    if (const char* e = std::getenv("DCTP_STACK_CFG")) { g.stack_cfg = std::atoi(e); if (g.stack_cfg < 4 || g.stack_cfg >= STACK_CFGS) g.stack_cfg = 4; }
+    if (const char* e = std::getenv("DCTP_STACK_CFG")) { g.stack_cfg = std::atoi(e); if (!stack_cfg_valid(g.stack_cfg)) g.stack_cfg = 0; }
     if (const char* e = std::getenv("DCTP_STACK")) g.stack_on = std::atoi(e) != 0;
     if (const char* e = std::getenv("DCTP_STACK_MIN_MB")) g.stack_min_bytes = static_cast<long long>(std::atoi(e)) << 20;
     if (const char* e = std::getenv("DCTP_TP")) g.t_prod = std::atoi(e) != 0;

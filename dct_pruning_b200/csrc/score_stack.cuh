@@ -99,21 +99,17 @@ struct StackSmem {
 // Every warp polls the mbarriers it depends on itself.  (Measured and dropped: one polling warp per role releasing its siblings
 // through a named barrier - the polls cost issue slots, the sleep behind mbarrier.try_wait being woken by any barrier event of
 // the CTA, but the extra hop costs more: 56x56 3.17 against 3.49 TB/s.)
-// RB: register rebalancing (setmaxnreg).  The roles need very different register counts - a converter thread ~40, an epilogue-1 thread
-// 64 for ONE TMEM round trip per tile instead of two (its busy time per tile is what sets the tile period: 1040 of ~1400 cycles, two
-// thirds of it waiting for tcgen05.ld) - but a CTA of 27 warps gets 72 each.  With RB the control warps are padded to a full warpgroup
-// (28 warps), converters, epilogue 2 and control give registers back and the epilogue-1 warpgroups take them (120).
 // NP8: Np / 8 as a compile-time constant (0: read it from the arguments) - epilogue 1's column loops lose their branches.
 // TRACE: the debug instantiation - the cycle accounting of DCTP_S_TRACE, the per-map energies (energy_out) and the coefficient dump
 // (coeff_out); the production instantiations carry none of that code (the host routes launches that ask for any of it here).
-template <int KP, int VEC, int NCONV, int NE1G, int NCG, int NE2G = 1, bool RB = false, int NP8 = 0, bool TRACE = false>
-__global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) * 32, 1) score_stack_kernel(const __grid_constant__ ScoreTensorMaps tmaps, const __grid_constant__ StackArgs a) {
+template <int KP, int VEC, int NCONV, int NE1G, int NCG, int NE2G = 1, int NP8 = 0, bool TRACE = false>
+__global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) score_stack_kernel(const __grid_constant__ ScoreTensorMaps tmaps, const __grid_constant__ StackArgs a) {
     using S = StackSmem;
     using namespace umma;
     constexpr int J = KP <= 32 ? 64 / KP : 1;
     constexpr int K1S = J * KP / 16, K2S = KP / 16;
     constexpr int G = KP == 16 ? 8 : KP == 32 ? 4 : 2, T2 = G / 2;
-    constexpr uint32_t W_E1 = NCONV, W_E2 = NCONV + 8 * NE1G, W_PROD = W_E2 + 4 * NE2G, W_MMA = W_PROD + 1, W_MMA2 = W_PROD + 2, NT = (W_MMA2 + (RB ? 2 : 1)) * 32;
+    constexpr uint32_t W_E1 = NCONV, W_E2 = NCONV + 8 * NE1G, W_PROD = W_E2 + 4 * NE2G, W_MMA = W_PROD + 1, W_MMA2 = W_PROD + 2, NT = (W_MMA2 + 1) * 32;
     constexpr uint32_t NCT = NCONV * 32 / NCG;                            // threads that convert one tile
     constexpr uint32_t TM_A = 0, TM_D1 = 32;                              // TMEM columns: A | D1 x 2 | A2 x 2 (64 each) | D2 x NB2 (64 each)
     const uint32_t d1_stride = a.ncols <= 112 ? 112u : 128u;
@@ -224,11 +220,8 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) *
 #define TR_ADD(acc) do { if (tr_me) { const long long now_ = clock64(); (acc) += now_ - tr_mark; tr_mark = now_; } } while (0)
 #define TR_FLUSH(base) do { if (tr_me) { a.trace[(base)] = tr0; a.trace[(base) + 1] = tr1; a.trace[(base) + 2] = tr2; a.trace[(base) + 3] = tr3; \
                                          a.trace[(base) + 4] = tr4; a.trace[(base) + 5] = tr5; } } while (0)
-    // (RB: the register hand-over sits at the top of every role's branch, so that the branch is compiled against its own count;
-    //  whole warpgroups - every role is a multiple of 4 warps with RB, the three control warps and a spare one share the last)
     if (warp == W_PROD) {
         // ================================================================ TMA producer
-        if constexpr (RB) reg_dealloc<24>();
         if (elect_one()) {
             tr_me = tr_on;
             uint32_t it = 0;
@@ -249,7 +242,6 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) *
         __syncwarp();
     } else if (warp == W_MMA) {
         // ================================================================ MMA issuer, stage 1: D1 = A * Bx^T (Bx_hi, then Bx_lo)
-        if constexpr (RB) reg_dealloc<24>();
         if (elect_one()) {
             tr_me = tr_on;
             const uint64_t desc = make_smem_desc(0, a.lbo1, 128, SWIZZLE_NONE);
@@ -281,7 +273,6 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) *
         __syncwarp();
     } else if (warp == W_MMA2) {
         // ================================================================ MMA issuer, stage 2: D2 = A2 * C^T (hi*hi + lo*hi + hi*lo)
-        if constexpr (RB) reg_dealloc<24>();
         if (elect_one()) {
             tr_me = tr_on;
             const uint64_t desc2 = make_smem_desc(0, S::LBO2, 128, SWIZZLE_NONE);
@@ -320,7 +311,6 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) *
         __syncwarp();
     } else if (warp < W_E1) {
         // ================================================================ converters: fp32 tile -> bf16 hi/lo -> Bx
-        if constexpr (RB) reg_dealloc<56>();
         const uint32_t cg = warp / (NCONV / NCG), ctid = tid - cg * NCT;     // converter group, thread within it
         uint32_t n = 0, it = 0;                                            // the CTA's tile number / its TMA sequence number
         int sg = 0;
@@ -414,7 +404,6 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) *
         TR_FLUSH(16);
     } else if (warp < W_E2) {
         // ================================================================ epilogue 1: D1 -> y = za + zb -> bf16 hi/lo -> A2
-        if constexpr (RB) reg_alloc<104>();
         const uint32_t q = warp & 3u, s = ((warp - W_E1) >> 2) & 1u, eg = (warp - W_E1) >> 3;
         const uint32_t lane_q = (q * 32u) << 16, lane_s = (q * 32u + s * 16u) << 16;
         const int np8 = NP8 ? NP8 : (a.Np >> 3);
@@ -441,50 +430,6 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) *
                 if (!ok) { dead = true; break; }
             }
             tc_fence_after_sync();
-            if constexpr (RB) {
-                // every column of D1 this warp needs (T2 maps x Np columns, both lane halves: 64 registers) is requested before the one
-                // wait: a TMEM load takes 200-350 cycles while the tensor core and the other warps use the same memory
-                constexpr int NG = KP / 8;
-                uint32_t za[T2][4 * NG], zb[T2][4 * NG];
-#pragma unroll
-                for (int t = 0; t < T2; ++t) {
-                    const uint32_t src_a = d1 + lane_q + (2 * t + s) * a.Np, src_b = src_a + (16u << 16);
-#pragma unroll
-                    for (int c8 = 0; c8 < NG; c8 += 2) {
-                        if (c8 + 2 <= np8) {
-                            tmem_ld_frag16(src_a + c8 * 8, reinterpret_cast<uint32_t (&)[8]>(za[t][4 * c8]));
-                            tmem_ld_frag16(src_b + c8 * 8, reinterpret_cast<uint32_t (&)[8]>(zb[t][4 * c8]));
-                        } else if (c8 < np8) {
-                            tmem_ld_frag8(src_a + c8 * 8, reinterpret_cast<uint32_t (&)[4]>(za[t][4 * c8]));
-                            tmem_ld_frag8(src_b + c8 * 8, reinterpret_cast<uint32_t (&)[4]>(zb[t][4 * c8]));
-                        }
-                    }
-                }
-                tmem_ld_wait();
-                TR_ADD(tr3);
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(d1_free + b);
-#pragma unroll
-                for (int t = 0; t < T2; ++t) {
-                    const uint32_t dst_hi = tmem + TM_A2 + b * 64 + t * KP + lane_s, dst_lo = dst_hi + KP / 2;
-#pragma unroll
-                    for (int c8 = 0; c8 < NG; c8 += 2) {
-                        if (c8 + 2 <= np8) {
-                            convert16(reinterpret_cast<const uint32_t (&)[8]>(za[t][4 * c8]), reinterpret_cast<const uint32_t (&)[8]>(zb[t][4 * c8]),
-                                      dst_hi + c8 * 4, dst_lo + c8 * 4);
-                        } else if (c8 < np8) {
-                            uint32_t h[2], l[2];
-#pragma unroll
-                            for (int i = 0; i < 2; ++i)
-                                split2_packed(add2_packed(pack2(za[t][4 * c8 + 2 * i], za[t][4 * c8 + 2 * i + 1]),
-                                                          pack2(zb[t][4 * c8 + 2 * i], zb[t][4 * c8 + 2 * i + 1])), h[i], l[i]);
-                            tmem_st_frag4(dst_hi + c8 * 4, h[0], h[1]);
-                            tmem_st_frag4(dst_lo + c8 * 4, l[0], l[1]);
-                        }
-                    }
-                }
-            } else {
 #pragma unroll
             for (int t = 0; t < T2; ++t) {
                 const uint32_t col0 = (2 * t + s) * a.Np;                 // this warp's map of A2 tile t
@@ -531,8 +476,6 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) *
                     }
                 }
             }
-            }
-            TR_ADD(tr4);
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
@@ -542,7 +485,6 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) *
         TR_FLUSH(24);
     } else if (warp < W_PROD) {
         // ================================================================ epilogue 2: D2 -> energies
-        if constexpr (RB) reg_dealloc<64>();
         const uint32_t q = warp & 3u, eg2 = (warp - W_E2) >> 2, et = tid - (W_E2 + 4 * eg2) * 32;      // group, thread within it
         const uint32_t lane_q = (q * 32u) << 16;
         const uint32_t s = lane >> 4, r = lane & 15u;
@@ -670,8 +612,6 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + (RB ? 4 : 3)) *
             TR_ADD(tr1);
         }
         TR_FLUSH(32);
-    } else if constexpr (RB) {
-        reg_dealloc<24>();                                                 // the spare warp of the control warpgroup
     }
 #undef TR_START
 #undef TR_ADD

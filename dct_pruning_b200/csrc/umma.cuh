@@ -111,15 +111,6 @@ __device__ __forceinline__ void fence_async_smem() {
 }
 
 // one lane of a converged warp (the compiler keeps the body on the uniform datapath)
-// Register rebalancing between the warpgroups of a warp-specialised CTA: every warp of a warpgroup (4 consecutive warps) executes it.
-template <uint32_t REGS>
-__device__ __forceinline__ void reg_alloc() {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
-}
-template <uint32_t REGS>
-__device__ __forceinline__ void reg_dealloc() {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
-}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(

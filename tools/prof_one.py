@@ -18,7 +18,7 @@ _lib.check(lib.dctp_init())
 x = torch.relu(torch.randn(B, C, H, W, device=dev))
 # rotate through enough copies that no launch finds its input in the 126 MB L2 (a single re-used tensor below that size
 # measures L2, not HBM - it made 7x7 look 35 % faster on one kernel than it is inside a real step)
-copies = [x] + [x.clone() for _ in range(max(0, int(400e6 // (x.numel() * 4))))]
+copies = [x] + ([] if os.environ.get('PROF_NOROT') else [x.clone() for _ in range(max(0, int(400e6 // (x.numel() * 4))))])   # PROF_NOROT=1: deliberately L2-resident
 acc = torch.zeros(C, dtype=torch.float64, device=dev)
 for _ in range(2):
     dct_energy(x, path=path, accum=acc, check=False)
