@@ -707,7 +707,8 @@ int ensure_init() {
     if (const char* e = std::getenv("DCTP_T_MIN_MB")) g.t_min_bytes = static_cast<long long>(std::atoi(e)) << 20;
     if (const char* e = std::getenv("DCTP_T_SLOTS")) g.t_slots = std::atoi(e);
     if (g.t_slots != 0) g.t_slots = 3;
-    CUDA_TRY(cudaFuncSetAttribute(score_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LargeSmem::TOTAL));
+    CUDA_TRY(cudaFuncSetAttribute(score_large_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LargeSmem::TOTAL));
+    CUDA_TRY(cudaFuncSetAttribute(score_large_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LargeSmem::TOTAL));
     CUDA_TRY(cudaFuncSetAttribute(score_simt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMT_SMALL_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(score_simt_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(rank_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RANK_SMEM_MAX));
@@ -761,7 +762,7 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
         if (!trace_buf) CUDA_TRY(cudaMalloc(&trace_buf, 16 * sizeof(long long)));
         a.trace = trace_buf;
     }
-    CUDA_TRY(launch_score(score_large_kernel, grid, LARGE_NT, LargeSmem::TOTAL, stream, a));
+    CUDA_TRY(launch_score((a.trace || a.dump) ? score_large_kernel<true> : score_large_kernel<false>, grid, LARGE_NT, LargeSmem::TOTAL, stream, a));
     if (energy_out) {
         sum_parts_kernel<<<(a.n_maps + 255) / 256, 256, 0, stream>>>(a.energy_parts, a.NVC, energy_out, a.n_maps);
         CUDA_TRY(cudaFreeAsync(a.energy_parts, stream));

@@ -74,6 +74,8 @@ constexpr int LARGE_CONV = 512;        // 16 converter / epilogue warps: warp w 
                                        // 16-column block (w / 4) of an epilogue
 constexpr int LARGE_NT = LARGE_CONV + 64;   // + the MMA issuer warp and the basis producer warp (one elected thread each)
 
+// TRACE: the cycle accounting of DCTP_L_TRACE and the coefficient dump; the production instantiation carries neither
+template <bool TRACE>
 __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeScoreArgs a) {
     constexpr int NC = LARGE_CONV;
     constexpr int XV = 2048 / NC;                                  // prefetch registers per map slab: float4 per thread
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
     uint64_t* d2_free = bars + 16;      // epilogue 2 has read D2 (16 warp arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_CTRL + 144);
     float* red = reinterpret_cast<float*>(smem + S::OFF_RED);
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (a shuffle: the compiler then knows it is warp-uniform)
     if ((smem_u32(smem) & 1023u) != 0) {
         if (tid == 0) atomicExch(a.status, DCTP_DEV_SMEM_ALIGN);
         return;
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
             uint32_t tile_par = 0, item_par = 0;
             bool first_item = true;
             long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            const bool tracing = a.trace != nullptr && blockIdx.x == 0;
+            const bool tracing = TRACE && a.trace != nullptr && blockIdx.x == 0;
             auto twait = [&](int slot, uint64_t* bar, uint32_t parity) {
                 if (tracing) {
                     const long long t0 = clock64();
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
         long long ctr[5] = {0, 0, 0, 0, 0};
         // one stage-1 step of this thread: wait for the buffer, convert + store the slab, hand it over, request the slab two steps on
         auto x_step = [&](uint32_t set, const float* xm, int h0, int w_next) {
-            const bool tr = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
+            const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && tid == 0;
             const long long t0 = tr ? clock64() : 0;
             if (xround >= 1) wait(x_empty + xp, (xround - 1) & 1u);       // the MMAs that last read this buffer are done
             const long long t1 = tr ? clock64() : 0;
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
                         const int u = c0 + i;
                         const float z = u < N ? __uint_as_float(r[i]) : 0.f;
                         e = fmaf(z, z, e);
-                        if (a.dump != nullptr && u < N) a.dump[(size_t)map * NN + (size_t)u * N + v0 + lane_idx] = z;
+                        if (TRACE && a.dump != nullptr && u < N) a.dump[(size_t)map * NN + (size_t)u * N + v0 + lane_idx] = z;
                     }
                 }
             }
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
             }
             named_bar_sync(1, NC);
         }
-        if (a.trace != nullptr && blockIdx.x == 0 && tid == 0)
+        if (TRACE && a.trace != nullptr && blockIdx.x == 0 && tid == 0)
             for (int i = 0; i < 5; ++i) a.trace[8 + i] = ctr[i];
     }
     tc_fence_before_sync();

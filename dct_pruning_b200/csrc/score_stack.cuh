@@ -40,9 +40,6 @@
 
 namespace dctp {
 
-#ifndef STACK_E1_BATCH
-#define STACK_E1_BATCH 4           // 8-column groups of D1 an epilogue-1 warp requests per TMEM round trip
-#endif
 constexpr int SCORE_MAX_SEG = 16;   // activations (hook sites of the same map side) one launch can score
 
 // One dense activation of a launch: all its scored maps back to back.  A launch walks the tiles of its segments in order;
@@ -430,48 +427,50 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
                 if (!ok) { dead = true; break; }
             }
             tc_fence_after_sync();
+            // The warp's share of D1 is T2 maps x (KP / 16) chunks of 16 columns (both lane halves: 8 + 8 registers a chunk).  Two chunks
+            // are requested per TMEM round trip (a load takes hundreds of cycles while the tensor core and the other warps use the same
+            // memory), whichever maps they belong to: two round trips a tile for every KP (one per map would be four at KP = 16).
+            constexpr int CPT = KP / 16, NCH = T2 * CPT;                   // chunks per map, chunks per tile
 #pragma unroll
-            for (int t = 0; t < T2; ++t) {
-                const uint32_t col0 = (2 * t + s) * a.Np;                 // this warp's map of A2 tile t
-                const uint32_t src_a = d1 + lane_q + col0, src_b = src_a + (16u << 16);
-                const uint32_t dst_hi = tmem + TM_A2 + b * 64 + t * KP + lane_s, dst_lo = dst_hi + KP / 2;
-                // all the map's columns are requested before the first wait (a TMEM load takes hundreds of cycles while the
-                // tensor core and the other epilogue warps use the same memory): one round trip per map instead of one per 16 columns
-                constexpr int NG = KP / 8, NB = STACK_E1_BATCH < NG ? STACK_E1_BATCH : NG;   // 8-column groups a map can have; groups per batch
+            for (int ch0 = 0; ch0 < NCH; ch0 += 2) {
+                uint32_t za[16], zb[16];
 #pragma unroll
-                for (int g0 = 0; g0 < NG; g0 += NB) {
-                    uint32_t za[4 * NB], zb[4 * NB];
-#pragma unroll
-                    for (int c = 0; c < NB; c += 2) {
-                        const int c8 = g0 + c;
+                for (int k = 0; k < 2; ++k) {
+                    const int ch = ch0 + k;
+                    if (ch < NCH) {
+                        const int t = ch / CPT, c8 = 2 * (ch % CPT);
+                        const uint32_t src_a = d1 + lane_q + (2 * t + s) * a.Np + c8 * 8, src_b = src_a + (16u << 16);
                         if (c8 + 2 <= np8) {
-                            tmem_ld_frag16(src_a + c8 * 8, reinterpret_cast<uint32_t (&)[8]>(za[4 * c]));
-                            tmem_ld_frag16(src_b + c8 * 8, reinterpret_cast<uint32_t (&)[8]>(zb[4 * c]));
+                            tmem_ld_frag16(src_a, reinterpret_cast<uint32_t (&)[8]>(za[8 * k]));
+                            tmem_ld_frag16(src_b, reinterpret_cast<uint32_t (&)[8]>(zb[8 * k]));
                         } else if (c8 < np8) {
-                            tmem_ld_frag8(src_a + c8 * 8, reinterpret_cast<uint32_t (&)[4]>(za[4 * c]));
-                            tmem_ld_frag8(src_b + c8 * 8, reinterpret_cast<uint32_t (&)[4]>(zb[4 * c]));
+                            tmem_ld_frag8(src_a, reinterpret_cast<uint32_t (&)[4]>(za[8 * k]));
+                            tmem_ld_frag8(src_b, reinterpret_cast<uint32_t (&)[4]>(zb[8 * k]));
                         }
                     }
-                    tmem_ld_wait();
-                    if (t == T2 - 1 && g0 + NB >= NG) {                   // every column of D1 this warp needs is in registers
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(d1_free + b);
-                    }
+                }
+                tmem_ld_wait();
+                if (ch0 + 2 >= NCH) {                                     // every column of D1 this warp needs is in registers
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d1_free + b);
+                }
 #pragma unroll
-                    for (int c = 0; c < NB; c += 2) {
-                        const int c8 = g0 + c;
+                for (int k = 0; k < 2; ++k) {
+                    const int ch = ch0 + k;
+                    if (ch < NCH) {
+                        const int t = ch / CPT, c8 = 2 * (ch % CPT);
+                        const uint32_t dst_hi = tmem + TM_A2 + b * 64 + t * KP + lane_s + c8 * 4, dst_lo = dst_hi + KP / 2;
                         if (c8 + 2 <= np8) {
-                            convert16(reinterpret_cast<const uint32_t (&)[8]>(za[4 * c]), reinterpret_cast<const uint32_t (&)[8]>(zb[4 * c]),
-                                      dst_hi + c8 * 4, dst_lo + c8 * 4);
+                            convert16(reinterpret_cast<const uint32_t (&)[8]>(za[8 * k]), reinterpret_cast<const uint32_t (&)[8]>(zb[8 * k]), dst_hi, dst_lo);
                         } else if (c8 < np8) {
                             uint32_t h[2], l[2];
 #pragma unroll
                             for (int i = 0; i < 2; ++i)
-                                split2_packed(add2_packed(pack2(za[4 * c + 2 * i], za[4 * c + 2 * i + 1]), pack2(zb[4 * c + 2 * i], zb[4 * c + 2 * i + 1])),
+                                split2_packed(add2_packed(pack2(za[8 * k + 2 * i], za[8 * k + 2 * i + 1]), pack2(zb[8 * k + 2 * i], zb[8 * k + 2 * i + 1])),
                                               h[i], l[i]);
-                            tmem_st_frag4(dst_hi + c8 * 4, h[0], h[1]);
-                            tmem_st_frag4(dst_lo + c8 * 4, l[0], l[1]);
+                            tmem_st_frag4(dst_hi, h[0], h[1]);
+                            tmem_st_frag4(dst_lo, l[0], l[1]);
                         }
                     }
                 }

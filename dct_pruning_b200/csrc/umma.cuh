@@ -291,12 +291,11 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 
 // ---------------------------------------------------------------- bf16 hi/lo split
 // x ~= hi + lo with hi = rn_bf16(x), lo = rn_bf16(x - hi): residual <= 2^-17 |x|
+__device__ __forceinline__ void split2_packed(uint64_t ab, uint32_t& hi, uint32_t& lo);
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    // cvt.rn.bf16x2.f32 d, x, y  packs x into the upper half and y into the lower half
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
-    float ra = a - __uint_as_float(hi << 16);
-    float rb = b - __uint_as_float(hi & 0xFFFF0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+    // (the packed form: when a and b sit in an even/odd register pair - two components of a 128-bit load - the residuals cost
+    //  one FADD2 instead of two FADDs; the bits are the same)
+    split2_packed((static_cast<uint64_t>(__float_as_uint(b)) << 32) | __float_as_uint(a), hi, lo);
 }
 
 // the same split for an fp32 pair held in a 64-bit register pair (a in the low word): the residual comes from one packed
