@@ -762,12 +762,37 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
         if (!trace_buf) CUDA_TRY(cudaMalloc(&trace_buf, 16 * sizeof(long long)));
         a.trace = trace_buf;
     }
-    CUDA_TRY(launch_score((a.trace || a.dump) ? score_large_kernel<true> : score_large_kernel<false>, grid, LARGE_NT, LargeSmem::TOTAL, stream, a));
+    // the activation as a 2-D tensor [n_maps * N rows, N floats]; a map slab is the box {64 floats, 128 rows}, out-of-range parts zero
+    if (static_cast<long long>(a.n_maps) * N >= (1ll << 31)) return fail(DCTP_E_INVALID, "too many maps of side %d in one call (tensor-map row coordinates are 32-bit)", N);
+    LargeTensorMap xmap;
+    {
+        std::memset(&xmap, 0, sizeof xmap);
+        cuuint64_t gdim[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(a.n_maps) * N};
+        cuuint64_t gstr[1] = {static_cast<cuuint64_t>(N) * 4};
+        cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
+        const CUresult r = reinterpret_cast<EncodeTiledFn>(g.encode_tiled)(
+            &xmap.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(first), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(DCTP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d maps of side %d", (int)r, a.n_maps, N);
+    }
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(grid));
+        cfg.blockDim = dim3(LARGE_NT);
+        cfg.dynamicSmemBytes = LargeSmem::TOTAL;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g.pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, (a.trace || a.dump) ? score_large_kernel<true> : score_large_kernel<false>, xmap, a));
+    }
     if (energy_out) {
         sum_parts_kernel<<<(a.n_maps + 255) / 256, 256, 0, stream>>>(a.energy_parts, a.NVC, energy_out, a.n_maps);
         CUDA_TRY(cudaFreeAsync(a.energy_parts, stream));
     }
-    note_kernel("score_large_kernel (tcgen05, tiled two-stage, 18 warps)");
+    note_kernel("score_large_kernel (tcgen05, tiled two-stage, TMA-staged map slabs, 19 warps)");
     if (tracing) {
         long long h[16];
         CUDA_TRY(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
@@ -776,8 +801,8 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
                         "basis slab %.0f (+%.0f look-ahead), A2 %.0f, D2 free %.0f\n",
                 N, h[7], h[6] / n, h[1] / n, h[4] / n, h[5] / n, h[2] / n, h[3] / n);
         const double m = h[12] > 0 ? double(h[12]) : 1.0;
-        fprintf(stderr, "[dctp trace] converter thread 0, cycles per map slab (%lld slabs): buffer wait %.0f, convert+store %.0f, "
-                        "fence+arrive %.0f, load issue %.0f\n", h[12], h[8] / m, h[9] / m, h[10] / m, h[11] / m);
+        fprintf(stderr, "[dctp trace] converter thread 0, cycles per map slab (%lld slabs): operand buffer wait %.0f, staged slab wait %.0f, "
+                        "convert + store + hand-over %.0f\n", h[12], h[8] / m, h[11] / m, h[9] / m);
     }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
     constexpr uint32_t TM_A = 0, TM_D = 256;
 
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // (shuffle: known warp-uniform)
     uint8_t* stg = smem;
     uint8_t* kr = smem + S::OFF_K;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);

@@ -26,13 +26,19 @@
 //   MMA issuer (one elected thread)     issues the MMAs of a step once its slabs are full and does nothing else: the
 //                                       tensor pipe's queue is shallow, every cycle this thread spends elsewhere is idle
 //                                       tensor time; tcgen05.commit frees the buffers
-//   16 converter / epilogue warps       map slabs fp32 -> bf16 hi/lo from registers loaded two steps earlier; the two
-//                                       epilogues.  No block-wide barrier inside the pipeline, only mbarriers.
-// One resident CTA of 18 warps per SM (226 KB of shared memory, 512 TMEM columns).
+//   map producer (one elected thread)   one cp.async.bulk.tensor.2d per map slab: the activation is a 2-D tensor [n_maps * N rows, N floats],
+//                                       a slab is the box {64 floats, 128 rows} at (w0, map * N + h0), landing row-major in a ring of two
+//                                       staging buffers; columns past N arrive as zeros (partial w blocks need no special path)
+//   16 converter / epilogue warps       staged fp32 slab -> bf16 hi/lo -> K-major operand slab; the two epilogues.
+//                                       No block-wide barrier inside the pipeline, only mbarriers.
+// One resident CTA of 19 warps per SM (226 KB of shared memory, 512 TMEM columns).
 #pragma once
+#include <cuda.h>
 #include "score_umma.cuh"
 
 namespace dctp {
+
+struct LargeTensorMap { CUtensorMap m; };   // the activation as [n_maps * N rows, N floats], box {64, 128}
 
 struct LargeScoreArgs {
     const float* x_dense;           // first scored element; all scored maps back to back (stride_h == N), 16-B aligned
@@ -61,10 +67,10 @@ struct LargeSmem {
                                                                    // tensor core), basis slab ring (a bulk copy takes about one step)
     static constexpr uint32_t OFF_A1 = 0;
     static constexpr uint32_t OFF_B = NXB * A1_BUF;
-    static constexpr uint32_t STAGE_BUF = 128 * 64 * 4;            // one fp32 map slab in flight (cp.async staging)
+    static constexpr uint32_t STAGE_BUF = 128 * 64 * 4;            // one fp32 map slab as the TMA delivers it: 128 rows x 64 floats
     static constexpr uint32_t OFF_STAGE = OFF_B + NBB * B_BUF;     // two of them
-    static constexpr uint32_t OFF_CTRL = OFF_STAGE + 2 * STAGE_BUF;   // 17 mbarriers, TMEM slot
-    static constexpr uint32_t OFF_RED = OFF_CTRL + 160;
+    static constexpr uint32_t OFF_CTRL = OFF_STAGE + 2 * STAGE_BUF;   // 21 mbarriers, TMEM slot
+    static constexpr uint32_t OFF_RED = OFF_CTRL + 192;
     static constexpr uint32_t TOTAL = OFF_RED + 512 * 4;
     static_assert(OFF_B % 1024 == 0 && B_BUF % 1024 == 0, "swizzle atoms are 1024-byte aligned");
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
@@ -72,13 +78,13 @@ struct LargeSmem {
 
 constexpr int LARGE_CONV = 512;        // 16 converter / epilogue warps: warp w owns TMEM lane quarter w % 4 and every 4th
                                        // 16-column block (w / 4) of an epilogue
-constexpr int LARGE_NT = LARGE_CONV + 64;   // + the MMA issuer warp and the basis producer warp (one elected thread each)
+constexpr int LARGE_NT = LARGE_CONV + 96;   // + the MMA issuer, basis producer and map producer warps (one elected thread each)
 
 // TRACE: the cycle accounting of DCTP_L_TRACE and the coefficient dump; the production instantiation carries neither
 template <bool TRACE>
-__global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeScoreArgs a) {
+__global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const __grid_constant__ LargeTensorMap xmap, const LargeScoreArgs a) {
     constexpr int NC = LARGE_CONV;
-    constexpr int XV = 2048 / NC;                                  // prefetch registers per map slab: float4 per thread
+    constexpr int XV = 2048 / NC;                                  // float4 per thread and map slab
     using S = LargeSmem;
     using namespace umma;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -92,7 +98,9 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
     uint64_t* acc_ready = bars + 14;    // D1 of an h-tile complete / D2 of an item complete
     uint64_t* a2_full = bars + 15;      // epilogue 1 wrote A2 into TMEM (16 warp arrivals)
     uint64_t* d2_free = bars + 16;      // epilogue 2 has read D2 (16 warp arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_CTRL + 144);
+    uint64_t* stg_full = bars + 17;     // [2] staged fp32 slab landed (TMA bytes)
+    uint64_t* stg_free = bars + 19;     // [2] the converters have read it (16 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_CTRL + 176);
     float* red = reinterpret_cast<float*>(smem + S::OFF_RED);
     const uint32_t tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (a shuffle: the compiler then knows it is warp-uniform)
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -109,6 +117,10 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
         for (uint32_t i = 0; i < S::NBB; ++i) {
             mbar_init(b_full + i, 1);
             mbar_init(b_empty + i, 1);
+        }
+        for (uint32_t i = 0; i < 2; ++i) {
+            mbar_init(stg_full + i, 1);
+            mbar_init(stg_free + i, NC / 32);
         }
         mbar_init(acc_ready, 1);
         mbar_init(a2_full, NC / 32);
@@ -256,6 +268,24 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
             }
         }
         __syncwarp();
+    } else if (warp == NC / 32 + 2) {
+        // =========================================================== map producer: one elected thread, one TMA per map slab,
+        //     in the order the converters consume them: (item, h-tile, 64-wide w block)
+        if (elect_one()) {
+            tma_prefetch_desc(&xmap.m);
+            uint32_t k = 0;
+            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+                const int row0 = (item / a.NVC) * N;
+                for (int h0 = 0; h0 < N; h0 += 128)
+                    for (int w0 = 0; w0 < N; w0 += 64, ++k) {
+                        const uint32_t set = k & 1u;
+                        if (k >= 2) wait(stg_free + set, ((k >> 1) - 1u) & 1u);
+                        mbar_arrive_expect_tx(stg_full + set, S::STAGE_BUF);
+                        tma_load_2d(smem + S::OFF_STAGE + set * S::STAGE_BUF, &xmap.m, w0, row0 + h0, stg_full + set);
+                    }
+            }
+        }
+        __syncwarp();
     } else {
         // =========================================================== converter / epilogue warps
         const uint32_t lane = tid & 31;
@@ -264,110 +294,59 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
         const uint32_t tmem_lane = tmem + (((warp & 3) * 32u) << 16);
         uint32_t xp = 0, xround = 0, acc_cnt = 0;                  // map slab ring position / wraps, accumulator hand-overs consumed
 
-        // Two map slabs are always in flight as cp.async copies into a per-thread staging area (fp32, the thread's own XV
-        // vectors per slab): no registers are tied up across the epilogues, and the copies are truly asynchronous.  Every
-        // load_x commits exactly one cp.async group and slabs are consumed in the order they were requested, so
-        // "all but the newest group have landed" (wait_group 1) is the right wait before a slab is converted.
+        // The staged slab is row-major [128 rows][64 floats]; thread t converts vectors t, t + 512, ...: row (i >> 4), float4 (i & 15),
+        // so a warp reads 512 contiguous bytes and the operand offset of a thread's vector is fixed up to + 32 rows per step.
         uint8_t* stage = smem + S::OFF_STAGE;
-        uint32_t xmeta[2] = {0, 0};                                // per set: float4 per row (low 8 bits) | vectors in the slab << 8
-        auto load_x = [&](uint32_t set, const float* xm, int h0, int w0) {
-            if (w0 < N) {
-                const int MH = min(128, N - h0), kvalid = min(64, N - w0);
-                const uint32_t vpr = kvalid / 4;                   // float4 vectors per row (4 / 8 / 12 / 16)
-                const uint32_t total = (uint32_t)MH * vpr;
-                if (set) xmeta[1] = vpr | (total << 8); else xmeta[0] = vpr | (total << 8);
-                const uint32_t dst = smem_u32(stage + set * S::STAGE_BUF) + tid * 16;
-                if (vpr == 16) {                                   // full-width block: row = i >> 4, fixed per thread
-                    const float4* src = reinterpret_cast<const float4*>(xm + (size_t)(h0 + (tid >> 4)) * N + w0) + (tid & 15);
-#pragma unroll
-                    for (int j = 0; j < XV; ++j)
-                        if (tid + j * NC < total) cp_async16(dst + j * NC * 16, src + (size_t)j * (NC / 16) * (N / 4));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < XV; ++j) {
-                        const uint32_t i = tid + j * NC;
-                        if (i < total) {
-                            const uint32_t r = i / vpr, q = i - r * vpr;
-                            cp_async16(dst + j * NC * 16, reinterpret_cast<const float4*>(xm + (size_t)(h0 + r) * N + w0) + q);
-                        }
-                    }
-                }
-            }
-            cp_async_commit();                                     // (an empty group when there is nothing left to load)
-        };
+        uint32_t xk = 0;                                           // map slabs consumed so far (staging buffer xk & 1)
         const uint32_t xoff16 = detail::kmajor_off(tid >> 4, (tid & 15) * 4, 128);    // full-width block: + j * 4096 B per 32 rows
         auto store_x = [&](uint32_t set, uint32_t p) {
-            const uint32_t meta = set ? xmeta[1] : xmeta[0];
-            const uint32_t vpr = meta & 255u, total = meta >> 8;
             uint8_t* hi = a1_base + p * S::A1_BUF;
             uint8_t* lo = hi + S::A1_HALF;
             const float4* src = reinterpret_cast<const float4*>(stage + set * S::STAGE_BUF) + tid;
-            cp_async_wait_but_one();
-            if (vpr == 16) {
+            float4 v[XV];
 #pragma unroll
-                for (int j = 0; j < XV; ++j)
-                    if (tid + j * NC < total) detail::Scatter<1>::st(hi + j * (NC / 16) * 128, lo + j * (NC / 16) * 128, static_cast<uint16_t>(xoff16), src[j * NC]);
-            } else {
+            for (int j = 0; j < XV; ++j) v[j] = src[j * NC];
 #pragma unroll
-                for (int j = 0; j < XV; ++j) {
-                    const uint32_t i = tid + j * NC;
-                    if (i < total) {
-                        const uint32_t r = i / vpr, q = i - r * vpr;
-                        detail::Scatter<1>::st(hi, lo, static_cast<uint16_t>(detail::kmajor_off(r, q * 4, 128)), src[j * NC]);
-                    }
-                }
-            }
+            for (int j = 0; j < XV; ++j)
+                detail::Scatter<1>::st(hi + j * (NC / 16) * 128, lo + j * (NC / 16) * 128, static_cast<uint16_t>(xoff16), v[j]);
         };
         long long ctr[5] = {0, 0, 0, 0, 0};
-        // one stage-1 step of this thread: wait for the buffer, convert + store the slab, hand it over, request the slab two steps on
-        auto x_step = [&](uint32_t set, const float* xm, int h0, int w_next) {
+        // one stage-1 step of this thread: wait for the operand buffer and the staged slab, convert + store, hand both over
+        auto x_step = [&]() {
             const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && tid == 0;
+            const uint32_t set = xk & 1u;
             const long long t0 = tr ? clock64() : 0;
             if (xround >= 1) wait(x_empty + xp, (xround - 1) & 1u);       // the MMAs that last read this buffer are done
             const long long t1 = tr ? clock64() : 0;
-            store_x(set, xp);
+            wait(stg_full + set, (xk >> 1) & 1u);
             const long long t2 = tr ? clock64() : 0;
+            store_x(set, xp);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stg_free + set);                   // (the slab is in registers / stored: the TMA may refill it)
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(x_full + xp);
-            const long long t3 = tr ? clock64() : 0;
-            load_x(set, xm, h0, w_next);
             if (tr) {
-                ctr[0] += t1 - t0; ctr[1] += t2 - t1; ctr[2] += t3 - t2; ctr[3] += clock64() - t3; ctr[4] += 1;
+                ctr[0] += t1 - t0; ctr[3] += t2 - t1; ctr[1] += clock64() - t2; ctr[4] += 1;
             }
+            ++xk;
             if (++xp == S::NXB) { xp = 0; ++xround; }
         };
 
         int item = blockIdx.x;
-        if (item < a.n_items) {                                    // operands of the very first steps
-            const float* xm = a.x_dense + (size_t)(item / a.NVC) * NN;
-            load_x(0, xm, 0, 0);
-            load_x(1, xm, 0, 64);
-        }
         const int NB = (N + 63) >> 6;                              // 64-wide w blocks per tile
         const int PS = min((int)S::NXB, NB);                       // slabs of the following tile stored ahead of time
         int first_block = 0;                                       // this tile's slabs [0, first_block) are already stored
         for (; item < a.n_items; item += gridDim.x) {
             const int map = item / a.NVC, vc = item - map * a.NVC;
             const int v0 = vc * 128, MV = min(128, N - v0);
-            const float* xm = a.x_dense + (size_t)map * NN;
             const int nitem = item + (int)gridDim.x;               // what this CTA works on next
-            const float* nxm = a.x_dense + (size_t)(nitem / a.NVC) * NN;
 
             for (int h0 = 0; h0 < N; h0 += 128) {
                 const int MH = min(128, N - h0);
-                // ---- stage 1 operands: X slab rows h0.., one step per 64-wide w block, register sets alternate
-                for (int b = first_block; b < NB; ++b) {             // (first_block is even: 0 or 4, or the tile is done)
-                    x_step(b & 1, xm, h0, (b + 2) * 64);
-                }
-                // the tile after this one (next h-tile, or the first of the next item): its first two slabs travel now
-                const bool more = h0 + 128 < N || nitem < a.n_items;
-                const float* txm = h0 + 128 < N ? xm : nxm;
-                const int th0 = h0 + 128 < N ? h0 + 128 : 0;
-                if (more) {
-                    load_x(0, txm, th0, 0);
-                    load_x(1, txm, th0, 64);
-                }
+                // ---- stage 1 operands: X slab rows h0.., one step per 64-wide w block
+                for (int b = first_block; b < NB; ++b) x_step();
+                const bool more = h0 + 128 < N || nitem < a.n_items;   // is there a tile after this one (next h-tile, or the next item's first)
                 // ---- epilogue 1: D1 row v (lane), columns h -> bf16 hi/lo pairs -> A2 over the same TMEM columns
                 wait(acc_ready, acc_cnt & 1u);                     // all stage-1 MMAs of the tile (and everything before) are complete
                 ++acc_cnt;
@@ -404,9 +383,7 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const LargeSco
                 //      third and fourth have the whole of stage 2 to arrive), so its stage 1 never waits for operands
                 first_block = 0;
                 if (more) {
-                    for (int b = 0; b < PS; ++b) {
-                        x_step(b & 1, txm, th0, (b + 2) * 64);
-                    }
+                    for (int b = 0; b < PS; ++b) x_step();
                     first_block = PS;
                 }
             }

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128 * (NSLOT + NPROD), 1) score_t_kernel(const
     constexpr int KB16 = N1MAX * 8;                                // 64-element K block of the data operand, in 16-byte units
     using Entry = typename detail::Scatter<VPE>::Entry;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (shuffle: the compiler then knows it is warp-uniform)
     const uint32_t wg = warp / WPS, wtid = tid - wg * TPS;         // tile slot of this warp set, thread within it
     const uint32_t swarp = warp - wg * WPS;                        // warp within the slot: lane quarter swarp & 3, column half swarp >> 2
     uint8_t* bx_hi = smem + wg * S::SLOT_BYTES;

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
     const typename detail::Scatter<VPE>::Entry* scat =
         reinterpret_cast<const typename detail::Scatter<VPE>::Entry*>(smem + S::OFF_VAR + a.red_bytes);  // dense modes
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (shuffle: the compiler then knows it is warp-uniform)
     if ((smem_u32(smem) & 1023u) != 0) {                           // SWIZZLE_128B atoms need 1024-B alignment
         if (tid == 0) atomicExch(a.status, DCTP_DEV_SMEM_ALIGN);
         return;
