@@ -306,26 +306,27 @@ int get_stack_basis(int N, StackBasis& out) {
 //   cfg 4: 8 converter warps in two groups (alternate tiles), 27 warps        cfg 7: 12 converter warps (two groups of 6), 31 warps
 //   cfg 6: cfg 4 with the debug outputs compiled in (DCTP_S_TRACE cycle accounting, per-map energies, coefficient dump); the host
 //          routes launches that ask for any of them here, production launches never
-// AUTO (cfg 0): cfg 7 for sides above 32 (56x56: 4.12 against 4.03 TB/s), cfg 4 below (no difference there, fewer registers taken).
+// AUTO (cfg 0): cfg 7 (56x56 4.14 against 4.06 TB/s for cfg 4, 14x14 3.55 against 3.45, 28x28 equal).
 // Layouts measured and retired in round 2 (same box, 56x56 / 28x28 / 14x14 TB/s, before the instruction diet): one epilogue-2 group
 // 3.73 / 3.47 / 3.19 (two: 3.73 / 3.62 / 3.25), two epilogue-1 groups 3.78 / 3.57 / 3.12, 4 converter warps 3.59 / 3.31 / 2.89;
-// after it: register rebalancing (setmaxnreg: converters 56, epilogue 1 104 registers and ONE TMEM round trip per tile) 3.36 against
+// after it: 16 converter warps with one epilogue-2 group 4.08 / 3.55 / 3.38 and two epilogue-1 groups with one epilogue-2 group 4.05 / 3.66 /
+// 3.40 (cfg 7: 4.14 / 3.99 / 3.55); register rebalancing (setmaxnreg: converters 56, epilogue 1 104 registers and ONE TMEM round trip per tile) 3.36 against
 // 3.61 at 56x56; converters reading global memory directly behind an L2 bulk prefetch instead of the TMA-staged copy 3.46 against 4.07.
 constexpr int STACK_CFGS = 8, STACK_VARIANTS = 10;
 typedef void (*StackKernel)(const ScoreTensorMaps, const StackArgs);
-template <bool TRACE, int NCONV>
+template <bool TRACE, int NCONV, int NE1G = 1, int NE2G = 2>
 StackKernel stack_kernel_of(int v) {
     switch (v) {
-        case 0: return score_stack_kernel<16, 4, NCONV, 1, 2, 2, 2, TRACE>;
-        case 1: return score_stack_kernel<16, 2, NCONV, 1, 2, 2, 2, TRACE>;
-        case 2: return score_stack_kernel<32, 4, NCONV, 1, 2, 2, 3, TRACE>;
-        case 3: return score_stack_kernel<32, 4, NCONV, 1, 2, 2, 4, TRACE>;
-        case 4: return score_stack_kernel<32, 2, NCONV, 1, 2, 2, 3, TRACE>;
-        case 5: return score_stack_kernel<32, 2, NCONV, 1, 2, 2, 4, TRACE>;
-        case 6: return score_stack_kernel<48, 4, NCONV, 1, 2, 2, 5, TRACE>;
-        case 7: return score_stack_kernel<48, 4, NCONV, 1, 2, 2, 6, TRACE>;
-        case 8: return score_stack_kernel<64, 4, NCONV, 1, 2, 2, 7, TRACE>;
-        default: return score_stack_kernel<64, 4, NCONV, 1, 2, 2, 8, TRACE>;
+        case 0: return score_stack_kernel<16, 4, NCONV, NE1G, 2, NE2G, 2, TRACE>;
+        case 1: return score_stack_kernel<16, 2, NCONV, NE1G, 2, NE2G, 2, TRACE>;
+        case 2: return score_stack_kernel<32, 4, NCONV, NE1G, 2, NE2G, 3, TRACE>;
+        case 3: return score_stack_kernel<32, 4, NCONV, NE1G, 2, NE2G, 4, TRACE>;
+        case 4: return score_stack_kernel<32, 2, NCONV, NE1G, 2, NE2G, 3, TRACE>;
+        case 5: return score_stack_kernel<32, 2, NCONV, NE1G, 2, NE2G, 4, TRACE>;
+        case 6: return score_stack_kernel<48, 4, NCONV, NE1G, 2, NE2G, 5, TRACE>;
+        case 7: return score_stack_kernel<48, 4, NCONV, NE1G, 2, NE2G, 6, TRACE>;
+        case 8: return score_stack_kernel<64, 4, NCONV, NE1G, 2, NE2G, 7, TRACE>;
+        default: return score_stack_kernel<64, 4, NCONV, NE1G, 2, NE2G, 8, TRACE>;
     }
 }
 bool stack_cfg_valid(int cfg) { return cfg == 4 || cfg == 6 || cfg == 7; }
@@ -419,7 +420,7 @@ int launch_stack(const SiteDesc* sites, int n, int N, float* energy_out, float* 
     }
     const int variant = stack_variant(KP, v4 ? 4 : 2, a.Np / 8);
     // per-map energies, coefficients and the cycle trace live in the debug instantiation (cfg 6) only
-    const int cfg = (a.energy_out || a.dump || tracing) ? 6 : g.stack_cfg ? g.stack_cfg : (KP > 32 ? 7 : 4);
+    const int cfg = (a.energy_out || a.dump || tracing) ? 6 : g.stack_cfg ? g.stack_cfg : 7;
     CUDA_TRY(launch_score_tma(stack_kernel_fn(cfg, variant), grid, stack_threads(cfg), smem, stream, maps, a));
     note_kernel("score_stack_kernel<KP=%d,VEC=%d,cfg%d> (tcgen05, stacked hi/lo basis in TMEM, TMA tile ring, warp specialised)", KP, basis.vec, cfg);
     if (tracing) {

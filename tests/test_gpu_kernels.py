@@ -124,6 +124,27 @@ def test_stacked_basis_kernel(lib, cuda_device, n):
     assert np.abs(co.cpu().numpy() - z).max() / np.abs(z).max() < 2e-5
 
 
+@pytest.mark.parametrize('n', [1, 3, 7, 8] + STACK_SIDES + [96, 160, 288, 320])
+def test_production_instantiations_match_oracle(lib, cuda_device, n):
+    """The launches above ask for per-map energies or coefficients, which the stacked-basis and large-map kernels only carry in their
+    debug instantiations.  Here nothing but the channel sums is requested - the instantiation every hook launch runs (AUTO's choice) -
+    on shapes with many tiles per CTA, a ragged last tile and more maps than one tile holds; per-channel sums vs float64."""
+    from dct_pruning_b200 import _lib
+    from dct_pruning_b200.ops import dct_energy
+    shapes = ((3, 150, n, n), (1, 5, n, n)) if n <= 64 else ((2, 40, n, n), (1, 3, n, n))
+    for shape in shapes:
+        x = relu_maps(shape, seed=1300 + n, dead_every=5)
+        acc, en, co = dct_energy(x.to(cuda_device), path='auto')
+        assert en is None and co is None
+        name = _lib.load().dctp_last_kernel().decode()
+        assert ('cfg6' not in name) and name, name                   # not the debug instantiation
+        want = port.energy_scipy64(x.numpy()).sum(0)
+        got = acc.cpu().numpy()
+        live = want > 0
+        assert (got[~live] == 0).all()
+        assert rel_err(got[live], want[live]).max() < ENERGY_TOL, (shape, name)
+
+
 @pytest.mark.parametrize('n', [4, 7, 8, 10, 14, 20, 28, 40, 56, 64, 80, 128])
 @pytest.mark.parametrize('path', ['umma', 'simt'])
 def test_coefficients_match_scipy(lib, cuda_device, n, path):
