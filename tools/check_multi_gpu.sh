@@ -8,9 +8,9 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127
     bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json
 tail -c 1500 gpurun_out/bench_n$N.json; echo
 rm -rf /tmp/s1 /tmp/sN
-python importance_generation.py --net resnet_56 --batch_size 64 --limit 3 --out_root /tmp/s1 --compress_rate '[0.]+[0.18]*29' > /dev/null
+python importance_generation.py --net resnet_56 --synthetic --random_init --batch_size 64 --limit 3 --out_root /tmp/s1 --compress_rate '[0.]+[0.18]*29' > /dev/null
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 \
-    importance_generation.py --net resnet_56 --batch_size 64 --limit 3 --out_root /tmp/sN --compress_rate '[0.]+[0.18]*29' > /dev/null
+    importance_generation.py --net resnet_56 --synthetic --random_init --batch_size 64 --limit 3 --out_root /tmp/sN --compress_rate '[0.]+[0.18]*29' > /dev/null
 python - <<PY
 import os, numpy as np
 a, b = '/tmp/s1/resnet_56_limit3', '/tmp/sN/resnet_56_limit3'
