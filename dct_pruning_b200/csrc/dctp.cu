@@ -89,9 +89,9 @@ struct State {
                                                        // (52x52, 56x56; DCTP_TP=0 turns it off): ResNet-50 step 3.30 -> 3.15 ms
     bool pdl = true;                                   // programmatic dependent launch of the score kernels (DCTP_PDL=0 disables)
     int t_auto_lo = 52;                                // sides from here up always go to the TMEM-operand kernel under AUTO (DCTP_T_LO)
-    int large_lo = 96;                                 // smallest side AUTO routes to the tiled large-map kernel (DCTP_LARGE_LO);
-                                                       // measured vs the smem-operand kernel, [12,64,N,N]: 80 0.66 vs 0.65, 96 0.87 vs 0.73,
-                                                       // 112 1.07 vs 0.77, 128 1.43 vs 0.89 TB/s
+    int large_lo = 80;                                 // smallest side AUTO routes to the tiled large-map kernel (DCTP_LARGE_LO);
+                                                       // measured vs the smem-operand kernel, [12,64,N,N]: 80 0.92 vs 0.67 TB/s (a tie in
+                                                       // round 1, before the large kernel lost a fifth of its instructions), 96 1.22 vs 0.73
     long long t_min_bytes = 32ll << 20;                // smaller sides only for launches of at least this many bytes (DCTP_T_MIN_MB)
     int regs[2][6][2] = {};                            // registers/thread per (KP, load mode, prefetch) instantiation
     // scratch of dctp_score_host (grow-only)

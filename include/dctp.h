@@ -41,7 +41,7 @@ extern "C" {
 #define DCTP_PATH_UMMA   1        /* tcgen05/TMEM bf16x3 kernel, operands in shared memory; square maps, side <= 128, contiguous maps */
 #define DCTP_PATH_SIMT   2        /* fp32 CUDA-core kernels; any H x W, strided rows */
 #define DCTP_PATH_TMEM   3        /* tcgen05 kernel with TMEM-resident operands; dense square maps, side 5..64 (odd sides up to 13) */
-#define DCTP_PATH_LARGE  4        /* tiled tcgen05 kernel; dense square maps, side 80..320, side % 16 == 0 (AUTO: from 96) */
+#define DCTP_PATH_LARGE  4        /* tiled tcgen05 kernel; dense square maps, side 80..320, side % 16 == 0 */
 #define DCTP_PATH_STACK  5        /* warp-specialised tcgen05 kernel, TMA-staged tiles, stacked hi/lo basis in TMEM; dense square maps,
                                      even side 10..64 (above 32: multiples of 4).  AUTO's choice for these shapes */
 #define DCTP_PATH_KRON   6        /* single-stage Kronecker tcgen05 kernel (C_N (x) C_N resident in shared memory, one map per TMEM

@@ -40,8 +40,9 @@ def test_version_and_path_selection(library):
     library.dctp_path_for.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong]
     assert library.dctp_path_for(56, 56, 56) == 1          # tensor-core path
     assert library.dctp_path_for(7, 7, 7) == 1
-    assert library.dctp_path_for(80, 80, 80) == 1
-    assert library.dctp_path_for(128, 128, 128) == 4        # from side 96 (multiples of 16) the tiled kernel is faster
+    assert library.dctp_path_for(80, 80, 80) == 4          # from side 80 (multiples of 16) the tiled kernel is faster
+    assert library.dctp_path_for(72, 72, 72) == 1
+    assert library.dctp_path_for(128, 128, 128) == 4
     assert library.dctp_path_for(100, 100, 100) == 1
     assert library.dctp_path_for(32, 16, 16) == 2          # non-square -> CUDA cores
     assert library.dctp_path_for(56, 56, 60) == 2          # strided rows -> CUDA cores
