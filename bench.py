@@ -73,6 +73,7 @@ def parse():
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--no-strong', action='store_true', help='skip the strong-scaling leg (global batch split over the ranks)')
     p.add_argument('--no-u2netp', action='store_true', help='skip the U^2-Netp 320/288 summary (BASELINE config 5)')
+    p.add_argument('--per-site', action='store_true', help='one launch per hook site in the timed steps too (no multi-site launches): the form the ncu launch list is taken in, so that bytes per launch compare with the per-site algorithmic bytes')
     p.add_argument('--graph', action='store_true', help='replay CUDA graphs (hook launches of a step; forward + hooks in the e2e leg): takes the host out of launch-bound nets')
     return p.parse_args()
 
@@ -190,7 +191,7 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
     net = get_network(net_name).to(device).eval()
     g = torch.Generator().manual_seed(1000 + rank)
     host_batch = torch.randn(max(B, 1), 3, side, side, generator=g)[:B].contiguous().pin_memory()
-    session = ScoreSession(net, net_name, path=args.path)
+    session = ScoreSession(net, net_name, path=args.path, defer_bytes=0 if getattr(args, 'per_site', False) else None)
     if world > 1:
         session.plan_layout(torch.zeros(1, 3, side, side, device=device))
     out = {'batch_per_gpu': B, 'input_side': side}

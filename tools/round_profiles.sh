@@ -11,8 +11,8 @@ for net in resnet_56 vgg_16_bn googlenet densenet_40; do
   python bench.py --net $net --steps 5 --warmup 3 --no-cpu-baseline --no-u2netp --graph > $O/${R}_bench_${net}_graph.json 2>> $O/${R}_bench_$net.err
 done
 # launch list of the bench command (per-launch durations are cold-cache and serialised: shares, not absolutes)
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
-  --log-file $O/${R}_launches_bench_resnet50.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-strong --no-u2netp > $O/${R}_ncu_launches.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"score_|topk_|finalize_" -c 400 --csv \
+  --log-file $O/${R}_launches_bench_resnet50.csv python bench.py --steps 2 --warmup 3 --per-site --no-cpu-baseline --no-e2e --no-strong --no-u2netp > $O/${R}_ncu_launches.log 2>&1
 cap() {  # name, kernel regex, prof_one arguments...
   local name=$1 k=$2; shift 2
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o /tmp/${R}_$name python tools/prof_one.py "$@" > $O/${R}_ncu_$name.log 2>&1
