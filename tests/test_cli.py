@@ -136,3 +136,24 @@ def test_prune_entry_selects_from_existing_score_files(lib, cuda_device, tmp_pat
                                 '--save_pruned', str(pruned)])
     assert {s.stem: [int(i) for i in idx] for s, idx in kept} == want
     assert torch.load(pruned)['layer1.0.conv1.weight'].shape[0] == int(16 * (1 - 0.18))
+
+
+def test_score_op_flag_and_session_argument():
+    """--score_op selects one of the per-slice reductions the reference keeps beside the DCT (utils/common.py:267-269); the default
+    is the DCT; an unknown op is refused before anything touches a device."""
+    from dct_pruning_b200.cli import build_parser
+    from dct_pruning_b200.hooks import ScoreSession
+    from dct_pruning_b200.zoo import get_network
+    p = build_parser()
+    assert p.parse_args([]).score_op == 'dct2'
+    for op in ('dct2', 'rank', 'rank_sq', 'dct3'):
+        assert p.parse_args(['--score_op', op]).score_op == op
+    with pytest.raises(SystemExit):
+        p.parse_args(['--score_op', 'svd'])
+    net = get_network('vgg_16_bn')
+    assert ScoreSession(net, 'vgg_16_bn', op='rank').op == 'rank'
+    with pytest.raises(ValueError):
+        ScoreSession(net, 'vgg_16_bn', op='svd')
+    with pytest.raises(RuntimeError):                        # no CPU path for the alternative ops either
+        s = ScoreSession(net, 'vgg_16_bn', op='rank')
+        s.score(0, torch.zeros(1, 4, 8, 8))
