@@ -164,10 +164,25 @@ def imp_score(net, args, loader=None, out_root='importance_score', write=True, p
     return files
 
 
+def npy_bytes(vec):
+    """The bytes `np.save` writes for a 1-D float32 vector (.npy format 1.0: magic, little-endian header length, the header dict
+    padded with spaces to a multiple of 64 bytes and ended by a newline, the data) - what the reference's np.save call (common.py:394)
+    produces and its prune_* scripts np.load.  Written out by hand because a run ends with one file per score vector (ResNet-50: 53)
+    and np.save's header formatting is most of what such a file costs; tests/test_abi.py compares with np.save and the shipped files."""
+    vec = np.ascontiguousarray(vec, dtype='<f4')
+    if vec.ndim != 1:
+        raise ValueError('score vectors are 1-D, got shape %s' % (vec.shape,))
+    head = "{'descr': '<f4', 'fortran_order': False, 'shape': (%d,), }" % vec.shape[0]
+    pad = -(10 + len(head) + 1) % 64
+    head = (head + ' ' * pad + '\n').encode('latin1')
+    return b'\x93NUMPY\x01\x00' + len(head).to_bytes(2, 'little') + head + vec.tobytes()
+
+
 def write_score_files(files, directory, verbose=True):
     os.makedirs(directory, exist_ok=True)
     for stem, vec in files.items():
-        np.save(os.path.join(directory, stem + '.npy'), np.ascontiguousarray(vec, dtype=np.float32))
+        with open(os.path.join(directory, stem + '.npy'), 'wb') as f:
+            f.write(npy_bytes(vec))
         if verbose:
             print(os.path.join(directory, stem) + ':done!')   # common.py:395
     return directory

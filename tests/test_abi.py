@@ -85,3 +85,11 @@ def test_npy_bytes_match_shipped_files(tmp_path):
         assert arr.dtype == np.float32 and len(raw) == 128 + 4 * arr.shape[0]
         write_score_files({'x': arr}, str(tmp_path))
         assert open(os.path.join(str(tmp_path), 'x.npy'), 'rb').read() == raw
+    # the hand-written writer against np.save itself, also where the shape's digits push the header over a 64-byte boundary
+    import io
+    from dct_pruning_b200.generate import npy_bytes
+    for n in (1, 9, 12, 64, 999, 1000, 22720, 10 ** 6):
+        v = np.arange(n, dtype=np.float32) * 0.5
+        ref = io.BytesIO()
+        np.save(ref, v)
+        assert npy_bytes(v) == ref.getvalue(), n
