@@ -13,8 +13,10 @@
 //   epi   thread = lane = map: sum of squares of its own N2 columns -> one fp64 atomicAdd; no second stage, no scatter table,
 //         no cross-lane reduction
 //
-// Warp specialised, one CTA per SM: warp 8 = TMA producer (ring of 3 tiles), warps 0-3 = converters (thread = map: fp32 row ->
-// bf16 hi/lo -> tcgen05.st), warp 9 = MMA issuer, warps 4-7 = epilogue.  TMEM: A ring 4 x 64 columns | D ring 4 x 64 columns.
+// Warp specialised, one CTA per SM, 18 warps: warps 0-7 = two groups of converters (thread = map: fp32 row -> bf16 hi/lo -> tcgen05.st;
+// group g takes the 128-map sub-tiles g, g + 2, ... of the CTA), warps 8-15 = two groups of epilogue warps (likewise), warp 16 = TMA
+// producer (ring of 3 tiles), warp 17 = MMA issuer.  TMEM: A ring 4 x 64 columns | D ring 4 x 64 columns.  (One group of each, 10
+// warps, ran the 7x7 layers at 3.7 TB/s with 42 % of the issue slots and 21 % of the tensor pipe busy: a latency chain.)
 // EVEN sides: 2-D tensor map over [n_maps, N^2] whose box is a few floats wider than a row (the excess is out of bounds and
 // arrives as zeros), so that a thread's 128-bit reads of its own row are free of bank conflicts.  ODD sides: rows are not
 // 16-byte multiples; the stream is viewed as [rows, 32 floats] (as in score_stack.cuh) and read with 32-bit loads (odd stride).
@@ -48,7 +50,7 @@ struct KronSmem {
     static constexpr uint32_t TOTAL = OFF_SLOT + 128;
 };
 
-constexpr int KRON_NT = 320;
+constexpr int KRON_NT = 576, KRON_W_PROD = 16, KRON_W_MMA = 17;
 
 template <int K2, bool EVEN>
 __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_constant__ ScoreTensorMaps tmaps, const __grid_constant__ KronArgs a) {
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
     uint8_t* kr = smem + S::OFF_K;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);
     uint64_t* stg_full = bars;            // [3] TMA landed
-    uint64_t* stg_free = bars + 3;        // [3] 4 converter warps
+    uint64_t* stg_free = bars + 3;        // [3] 8 converter warps
     uint64_t* a_full = bars + 6;          // [4] 4 converter warps
     uint64_t* a_free = bars + 10;         // [4] the MMAs that read the slot have completed
     uint64_t* d_full = bars + 14;         // [4]
@@ -72,20 +74,20 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_SLOT);
 
     // barriers and TMEM first: the producer warp then has tiles on their way while the other warps stage the Kronecker basis
-    if (warp == 9) tmem_alloc<512>(tmem_slot);
+    if (warp == KRON_W_MMA) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        for (int s = 0; s < 3; ++s) { mbar_init(stg_full + s, 1); mbar_init(stg_free + s, 4); }
+        for (int s = 0; s < 3; ++s) { mbar_init(stg_full + s, 1); mbar_init(stg_free + s, 8); }
         for (int s = 0; s < 4; ++s) { mbar_init(a_full + s, 4); mbar_init(a_free + s, 1); mbar_init(d_full + s, 1); mbar_init(d_free + s, 4); }
         mbar_init_fence();
     }
-    if (warp == 8 && lane == 0) tma_prefetch_desc(&tmaps.m[0]);
+    if (warp == KRON_W_PROD && lane == 0) tma_prefetch_desc(&tmaps.m[0]);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     launch_dependents();
-    if (warp != 8) {
-        const uint32_t ptid = tid < 256 ? tid : tid - 32;
+    if (warp != KRON_W_PROD) {
+        const uint32_t ptid = tid < KRON_W_PROD * 32 ? tid : tid - 32;
         for (uint32_t off = ptid * 16; off < HALF; off += (KRON_NT - 32) * 16) {
             *reinterpret_cast<uint4*>(kr + off) = *reinterpret_cast<const uint4*>(a.k_hi + off);
             *reinterpret_cast<uint4*>(kr + HALF + off) = *reinterpret_cast<const uint4*>(a.k_lo + off);
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
         break;                                       \
     }
 
-    if (warp == 8) {
+    if (warp == KRON_W_PROD) {
         // ================================================================ TMA producer
         if (elect_one()) {
             uint32_t it = 0;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == KRON_W_MMA) {
         // ================================================================ MMA issuer
         if (elect_one()) {
             const uint64_t desc = make_smem_desc(0, LBO, 128, SWIZZLE_NONE);
@@ -149,9 +151,10 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
                 }
         }
         __syncwarp();
-    } else if (warp < 4) {
+    } else if (warp < 8) {
         // ================================================================ converters: thread = map, fp32 row -> bf16 hi | lo -> A (TMEM)
-        const uint32_t lane_bits = (warp * 32u) << 16;
+        const uint32_t grp = warp >> 2, gt = tid & 127u;                   // group, thread within it = map within a sub-tile
+        const uint32_t lane_bits = ((warp & 3u) * 32u) << 16;
         uint32_t it = 0, j = 0;
         int sg = 0;
         for (int tile = first; tile < a.num_tiles && !dead; tile += stride) {
@@ -163,25 +166,26 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
                 KRON_WAIT(stg_full + s, (it / S::NSTG) & 1u);
             }
             for (int st = 0; st < a.sub_tiles; ++st, ++j) {
+                if ((j & 1u) != grp) continue;                            // the other group's sub-tile
                 const uint32_t sl = j & 3u;
                 if (j >= 4) KRON_WAIT(a_free + sl, ((j >> 2) - 1u) & 1u);
                 tc_fence_after_sync();
                 float v[K2];
                 if (from_global) {
-                    const long long e0 = (static_cast<long long>(tile - a.seg.tile0[sg]) * a.tile_maps + st * 128 + tid) * a.NN;
+                    const long long e0 = (static_cast<long long>(tile - a.seg.tile0[sg]) * a.tile_maps + st * 128 + gt) * a.NN;
                     const long long total = a.seg.total_elems[sg];
                     const float* xs = a.seg.x[sg];
 #pragma unroll
                     for (int i = 0; i < K2; ++i) v[i] = (i < a.NN && e0 + i < total) ? xs[e0 + i] : 0.f;
                 } else if constexpr (EVEN) {
-                    const float4* row = reinterpret_cast<const float4*>(stg + s * S::STG_STRIDE) + static_cast<uint32_t>(st * 128 + tid) * (a.row_floats >> 2);
+                    const float4* row = reinterpret_cast<const float4*>(stg + s * S::STG_STRIDE) + static_cast<uint32_t>(st * 128 + gt) * (a.row_floats >> 2);
 #pragma unroll
                     for (int i = 0; i < K2 / 4; ++i) {
                         const float4 q4 = 4 * i < a.NN ? row[i] : make_float4(0.f, 0.f, 0.f, 0.f);
                         v[4 * i] = q4.x; v[4 * i + 1] = q4.y; v[4 * i + 2] = q4.z; v[4 * i + 3] = q4.w;
                     }
                 } else {
-                    const float* row = reinterpret_cast<const float*>(stg + s * S::STG_STRIDE) + static_cast<uint32_t>(st * 128 + tid) * a.NN;
+                    const float* row = reinterpret_cast<const float*>(stg + s * S::STG_STRIDE) + static_cast<uint32_t>(st * 128 + gt) * a.NN;
 #pragma unroll
                     for (int i = 0; i < K2; ++i) v[i] = i < a.NN ? row[i] : 0.f;
                 }
@@ -208,9 +212,9 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
                 ++it;
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < 16) {
         // ================================================================ epilogue: thread = map, energy of its own row of D
-        const uint32_t et = tid - 128;
+        const uint32_t grp = (warp >> 2) & 1u, et = tid & 127u;
         const uint32_t lane_bits = ((warp & 3u) * 32u) << 16;
         uint32_t j = 0;
         int sg = 0;
@@ -219,6 +223,7 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
             const uint32_t C = static_cast<uint32_t>(a.seg.c_count[sg]), seg_maps = static_cast<uint32_t>(a.seg.n_maps[sg]);
             double* const accum = a.seg.accum[sg];
             for (int st = 0; st < a.sub_tiles; ++st, ++j) {
+                if ((j & 1u) != grp) continue;
                 const uint32_t sl = j & 3u;
                 KRON_WAIT(d_full + sl, (j >> 2) & 1u);
                 tc_fence_after_sync();
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 9) tmem_dealloc<512>(tmem);
+    if (warp == KRON_W_MMA) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace dctp
