@@ -228,27 +228,28 @@ __global__ void __launch_bounds__(KRON_NT, 1) score_kron_kernel(const __grid_con
                 KRON_WAIT(d_full + sl, (j >> 2) & 1u);
                 tc_fence_after_sync();
                 const uint32_t m = static_cast<uint32_t>(tile - a.seg.tile0[sg]) * a.tile_maps + st * 128 + et;   // map within its segment
-                float e0 = 0.f, e1 = 0.f;
+                // the lane's K2 coefficients in ONE TMEM round trip; D is handed back as soon as they have landed
+                uint32_t z[K2];
 #pragma unroll
-                for (int c = 0; c < K2; c += 16) {
-                    uint32_t z[16];
-                    tmem_ld16(tmem + TM_D + sl * 64 + lane_bits + c, z);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        e0 = fmaf(__uint_as_float(z[i]), __uint_as_float(z[i]), e0);
-                        e1 = fmaf(__uint_as_float(z[8 + i]), __uint_as_float(z[8 + i]), e1);
-                    }
-                    if (a.dump != nullptr && m < seg_maps)
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (c + i < a.NN) a.dump[static_cast<long long>(m) * a.NN + c + i] = __uint_as_float(z[i]);
-                }
+                for (int c = 0; c < K2; c += 16) tmem_ld16(tmem + TM_D + sl * 64 + lane_bits + c, reinterpret_cast<uint32_t (&)[16]>(z[c]));
+                tmem_ld_wait();
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_free + sl);
+                float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+#pragma unroll
+                for (int c = 0; c < K2; c += 4) {
+                    e0 = fmaf(__uint_as_float(z[c]), __uint_as_float(z[c]), e0);
+                    e1 = fmaf(__uint_as_float(z[c + 1]), __uint_as_float(z[c + 1]), e1);
+                    e2 = fmaf(__uint_as_float(z[c + 2]), __uint_as_float(z[c + 2]), e2);
+                    e3 = fmaf(__uint_as_float(z[c + 3]), __uint_as_float(z[c + 3]), e3);
+                }
+                if (a.dump != nullptr && m < seg_maps)
+#pragma unroll
+                    for (int i = 0; i < K2; ++i)
+                        if (i < a.NN) a.dump[static_cast<long long>(m) * a.NN + i] = __uint_as_float(z[i]);
                 if (m < seg_maps) {
-                    const float e = e0 + e1;
+                    const float e = (e0 + e1) + (e2 + e3);
                     atomicAdd(accum + (m % C), static_cast<double>(e));
                     if (a.energy_out) a.energy_out[m] = e;
                 }
