@@ -433,6 +433,7 @@ int launch_stack(const SiteDesc* sites, int n, int N, float* energy_out, float* 
                         "epi2: wait D2 %.0f, TMEM loads %.0f, sums+shuffles %.0f, atomics %.0f\n",
                 N, cfg, h[14], h[0] / nt, h[16] / nt, h[17] / nt, h[18] / nt, h[19] / nt, h[8] / nt, h[9] / nt, h[10] / nt, h[40] / nt,
                 h[41] / nt, h[42] / nt, h[24] / nt, h[25] / nt, h[26] / nt, h[32] / nt, h[34] / nt, h[35] / nt, h[33] / nt);
+        fprintf(stderr, "[dctp trace] CTA 0, ns since kernel entry: TMEM + barriers ready %lld, bases staged and dependency wait over %lld, tile loop %lld\n", h[52], h[53], h[51]);
         fprintf(stderr, "[dctp trace] tile loop of CTA 0: %lld SM cycles in %lld ns = %.0f MHz, %.0f cycles per tile\n", h[50], h[51],
                 h[51] > 0 ? 1e3 * double(h[50]) / double(h[51]) : 0.0, double(h[50]) / nt);
     }

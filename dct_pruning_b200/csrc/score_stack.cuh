@@ -136,6 +136,8 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
     uint64_t* d2_free = bars + 20;                                        // [2] 4 epilogue-2 warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_SLOT);
 
+    long long tr_entry = 0;                                               // (debug instantiation) wall-clock stamps of the launch's phases
+    if (TRACE && a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_entry));
     // ---- prologue (independent of the activation).  Barriers and TMEM first: once they exist the producer warp goes ahead and has
     //      the first three tiles on their way from HBM while the other warps stage the bases and zero the operand buffers.
     if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
@@ -155,24 +157,45 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     launch_dependents();                                                  // this CTA holds its TMEM columns (see score_umma.cuh)
+    if (TRACE && a.trace != nullptr && blockIdx.x == 0 && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[52] = t_ - tr_entry; }
     if (warp != W_PROD) {
         const uint32_t ptid = tid < W_PROD * 32 ? tid : tid - 32;          // thread index among the NT - 32 staging threads
         constexpr uint32_t PNT = NT - 32;
-        for (uint32_t off = ptid * 16; off < 4 * S::BX_HALF; off += PNT * 16) *reinterpret_cast<uint4*>(bx + off) = make_uint4(0, 0, 0, 0);
-        for (uint32_t off = ptid * 16; off < S::C2_HALF; off += PNT * 16) {
-            *reinterpret_cast<uint4*>(c2 + off) = *reinterpret_cast<const uint4*>(a.c2_hi + off);
-            *reinterpret_cast<uint4*>(c2 + S::C2_HALF + off) = *reinterpret_cast<const uint4*>(a.c2_lo + off);
+        // Every global load of the prologue is issued before the first store (the stores are to shared memory / TMEM, which the compiler
+        // will not move loads across): one exposed L2 / HBM latency instead of four - 3.4 -> ~1.5 us of the ~10 us a launch costs beyond
+        // its bytes, which is what the 6-50 MB launches of the small layers are made of.
+        static_assert(2 * PNT * 16 >= S::C2_HALF && PNT * 16 >= S::TABLE_MAX, "prologue loads are unrolled for these sizes");
+        uint4 c2h[2], c2l[2], tb = make_uint4(0, 0, 0, 0), ai[8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t off = (ptid + i * PNT) * 16;
+            if (off < S::C2_HALF) {
+                c2h[i] = *reinterpret_cast<const uint4*>(a.c2_hi + off);
+                c2l[i] = *reinterpret_cast<const uint4*>(a.c2_lo + off);
+            }
         }
-        for (uint32_t off = ptid * 16; off < a.table_bytes; off += PNT * 16)
-            *reinterpret_cast<uint4*>(smem + S::OFF_TABLE + off) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.table) + off);
+        if (ptid * 16 < a.table_bytes) tb = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.table) + ptid * 16);
+        if (warp < 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ai[i] = reinterpret_cast<const uint4*>(a.a_img + tid * 32)[i];
+        }
+        for (uint32_t off = ptid * 16; off < 4 * S::BX_HALF; off += PNT * 16) *reinterpret_cast<uint4*>(bx + off) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t off = (ptid + i * PNT) * 16;
+            if (off < S::C2_HALF) {
+                *reinterpret_cast<uint4*>(c2 + off) = c2h[i];
+                *reinterpret_cast<uint4*>(c2 + S::C2_HALF + off) = c2l[i];
+            }
+        }
+        if (ptid * 16 < a.table_bytes) *reinterpret_cast<uint4*>(smem + S::OFF_TABLE + ptid * 16) = tb;
         if (warp < 4) {                                                   // the stacked basis -> TMEM columns [0,32)
-            uint32_t v[16];
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
-                const uint4* src = reinterpret_cast<const uint4*>(a.a_img + tid * 32 + part * 16);
+                uint32_t v[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint4 q4 = src[i];
+                    const uint4 q4 = ai[4 * part + i];
                     v[4 * i] = q4.x; v[4 * i + 1] = q4.y; v[4 * i + 2] = q4.z; v[4 * i + 3] = q4.w;
                 }
                 tmem_st16(tmem + ((warp * 32u) << 16) + TM_A + part * 16, v);
@@ -197,6 +220,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
     if (TRACE && a.trace != nullptr && blockIdx.x == 0 && tid == 0) {
         tr_c0 = clock64();
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_g0));
+        a.trace[53] = tr_g0 - tr_entry;                                   // TMEM + barriers + bases staged + the preceding kernel complete
     }
     const int first = blockIdx.x, stride = gridDim.x;
     const uint32_t tile_bytes = static_cast<uint32_t>(a.tile_rows) * 128u;
