@@ -23,12 +23,14 @@
 //             warps of a map -> one fp64 atomicAdd per map
 //
 // Tensor-core time per 25 KB of input: 448 + 384 cycles at 56x56 (score_tmem.cuh: 672 + 384), 512 + 192 at 28x28,
-// 512 + 96 at 14x14, against 1113 cycles of HBM time at the measured 6.55 TB/s.
+// 512 + 96 at 14x14, against 940-1113 cycles of HBM time at the measured 6.55 TB/s (the SM clock under this load is 1.65-1.7 GHz, not the
+// 1.965 GHz nvidia-smi shows).
 //
 // The kernel is warp specialised (one CTA per SM), every hand-over is an mbarrier.  Roles, in warp order:
-//   converters  NCONV warps: fp32 tile -> bf16 hi/lo -> Bx (two buffers), offsets from a host-built table
-//   epilogue 1  NE1G groups of 8 warps (warp = lane quarter q x row slot s); group g takes the CTA's tiles g, g + NE1G, ...
-//   epilogue 2  4 warps
+//   converters  NCONV warps (12 in production) in NCG = 2 groups that alternate tiles: fp32 tile -> bf16 hi/lo -> Bx (two buffers),
+//               offsets from a host-built table
+//   epilogue 1  NE1G groups of 8 warps (one in production; warp = lane quarter q x row slot s); group g takes the CTA's tiles g, g + NE1G, ...
+//   epilogue 2  NE2G groups of 4 warps (two in production) that alternate tiles
 //   producer    1 warp (one thread): one cp.async.bulk.tensor.2d per tile (tensor map over the dense fp32 stream viewed as
 //               [rows, 32 floats]; a tile is a box of tile_rows rows; rows past the end arrive as zeros) into a ring of 3
 //   issuers     2 warps (one thread each): stage 1 and stage 2 have their own issuing thread, so that neither the waits nor
@@ -91,7 +93,7 @@ struct StackSmem {
 
 
 // KP: contraction length per map (N rounded up to 16); VEC: granularity of a row in the fp32 stream (4: N % 4 == 0, 2: N even)
-// NCONV: converter warps (4 or 8) in NCG groups (group g converts the CTA's tiles g, g + NCG, ...); NE1G / NE2G: epilogue-1 / epilogue-2
+// NCONV: converter warps (8 or 12) in NCG groups (group g converts the CTA's tiles g, g + NCG, ...); NE1G / NE2G: epilogue-1 / epilogue-2
 // groups (1 or 2; group g takes the CTA's tiles g, g + 2, ...).
 // Every warp polls the mbarriers it depends on itself.  (Measured and dropped: one polling warp per role releasing its siblings
 // through a named barrier - the polls cost issue slots, the sleep behind mbarrier.try_wait being woken by any barrier event of
