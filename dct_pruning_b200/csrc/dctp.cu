@@ -744,18 +744,32 @@ int pick_vec(const float* x, long long stride_b, long long stride_c, int c_begin
 bool large_shape_supported(int H, int W, long long stride_h) { return H == W && H >= 80 && H <= 320 && (H % 16) == 0 && stride_h == W; }
 bool large_shape_ok(int H, int W, long long stride_h) { return large_shape_supported(H, W, stride_h) && H >= g.large_lo; }
 
-int launch_large(const float* first, int B, int N, int c_count, double* accum, float* energy_out, float* coeff_out, cudaStream_t stream) {
+// up to LARGE_MAX_SEG dense activations of side N in ONE launch (energy_out / coeff_out: single-site launches only)
+int launch_large(const SiteDesc* sites, int n, int N, float* energy_out, float* coeff_out, cudaStream_t stream) {
     LargeBasis basis;
     int rc = get_large_basis(N, basis);
     if (rc) return rc;
     LargeScoreArgs a;
     std::memset(&a, 0, sizeof a);
-    a.x_dense = first; a.n_maps = B * c_count; a.c_count = c_count;
     a.N = N; a.NPR = basis.NPR; a.NVC = (N + 127) / 128;
     large_u_chunks(N, a.NU, a.NUC);
-    a.n_items = a.n_maps * a.NVC;
+    a.seg.n_seg = n;
+    long long items = 0;
+    for (int i = 0; i < n; ++i) {
+        const long long maps = static_cast<long long>(sites[i].B) * sites[i].c_count;
+        if (maps * N >= (1ll << 31) || items + maps * a.NVC >= (1ll << 31))
+            return fail(DCTP_E_INVALID, "too many maps of side %d in one launch (tensor-map row coordinates and work-item numbers are 32-bit)", N);
+        a.seg.item0[i] = static_cast<int>(items);
+        a.seg.c_count[i] = sites[i].c_count;
+        a.seg.accum[i] = sites[i].accum;
+        a.n_maps += static_cast<int>(maps);
+        items += maps * a.NVC;
+    }
+    for (int i = n; i <= LARGE_MAX_SEG; ++i) a.seg.item0[i] = static_cast<int>(items);
+    a.n_items = static_cast<int>(items);
     a.c_hi = reinterpret_cast<const uint8_t*>(basis.hi); a.c_lo = reinterpret_cast<const uint8_t*>(basis.lo);
-    a.accum = accum; a.energy_out = energy_out; a.dump = coeff_out; a.status = g.status;
+    a.energy_out = n == 1 ? energy_out : nullptr; a.dump = n == 1 ? coeff_out : nullptr; a.status = g.status;
+    energy_out = a.energy_out;
     if (energy_out) CUDA_TRY(cudaMallocAsync(&a.energy_parts, sizeof(float) * a.n_maps * a.NVC, stream));   // (debug / parity output only)
     int grid = g.sm_count < a.n_items ? g.sm_count : a.n_items;
     static long long* trace_buf = nullptr;
@@ -764,19 +778,19 @@ int launch_large(const float* first, int B, int N, int c_count, double* accum, f
         if (!trace_buf) CUDA_TRY(cudaMalloc(&trace_buf, 16 * sizeof(long long)));
         a.trace = trace_buf;
     }
-    // the activation as a 2-D tensor [n_maps * N rows, N floats]; a map slab is the box {64 floats, 128 rows}, out-of-range parts zero
-    if (static_cast<long long>(a.n_maps) * N >= (1ll << 31)) return fail(DCTP_E_INVALID, "too many maps of side %d in one call (tensor-map row coordinates are 32-bit)", N);
+    // every activation as a 2-D tensor [n_maps * N rows, N floats]; a map slab is the box {64 floats, 128 rows}, out-of-range parts zero
     LargeTensorMap xmap;
-    {
-        std::memset(&xmap, 0, sizeof xmap);
-        cuuint64_t gdim[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(a.n_maps) * N};
+    std::memset(&xmap, 0, sizeof xmap);
+    for (int i = 0; i < n; ++i) {
+        cuuint64_t gdim[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(sites[i].B) * sites[i].c_count * N};
         cuuint64_t gstr[1] = {static_cast<cuuint64_t>(N) * 4};
         cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
         const CUresult r = reinterpret_cast<EncodeTiledFn>(g.encode_tiled)(
-            &xmap.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(first), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            &xmap.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sites[i].first), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(DCTP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for %d maps of side %d", (int)r, a.n_maps, N);
+        if (r != CUDA_SUCCESS) return fail(DCTP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for site %d, side %d", (int)r, i, N);
     }
+    for (int i = n; i < LARGE_MAX_SEG; ++i) xmap.m[i] = xmap.m[0];
     {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -1177,7 +1191,8 @@ int dctp_score_accum(const float* x, int B, int H, int W, long long stride_b, lo
                     return launch_simt(x, B, H, W, stride_b, stride_c, stride_h, c_begin, c_count, accum, energy_out, coeff_out, s);
                 return fail(DCTP_E_UNSUPPORTED, "large-map path takes dense 16-B aligned square maps, side 80..320 multiple of 16 (got %dx%d)", H, W);
             }
-            return launch_large(first, B, H, c_count, accum, energy_out, coeff_out, s);
+            const SiteDesc one = {first, B, c_count, accum};
+            return launch_large(&one, 1, H, energy_out, coeff_out, s);
         }
         case DCTP_PATH_SIMT:
             return launch_simt(x, B, H, W, stride_b, stride_c, stride_h, c_begin, c_count, accum, energy_out, coeff_out, s);
@@ -1200,20 +1215,21 @@ int dctp_score_accum_multi(const dctp_site* sites, int n_sites, int H, int W, vo
         }
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         const bool kron = H == W && H <= 8 && g.kron_on, stack = H == W && g.stack_on && stack_shape_supported(H);
+        const bool large = !kron && !stack && large_shape_ok(H, W, W);
         // one launch per SCORE_MAX_SEG sites; shapes the multi-site kernels do not take, and sites that are not 16-byte aligned,
         // go through the single-site entry below
         SiteDesc batch[SCORE_MAX_SEG];
         int nb = 0;
         for (int i = 0; i < n_sites; ++i) {
             if (sites[i].B == 0 || sites[i].c_count == 0) continue;
-            if (!(kron || stack) || (reinterpret_cast<uintptr_t>(sites[i].x) % 16) != 0) { single.push_back(i); continue; }
+            if (!(kron || stack || large) || (reinterpret_cast<uintptr_t>(sites[i].x) % 16) != 0) { single.push_back(i); continue; }
             batch[nb++] = SiteDesc{sites[i].x, sites[i].B, sites[i].c_count, sites[i].accum};
             if (nb == SCORE_MAX_SEG || i == n_sites - 1) {
-                if ((rc = kron ? launch_kron(batch, nb, H, nullptr, nullptr, s) : launch_stack(batch, nb, H, nullptr, nullptr, s))) return rc;
+                if ((rc = kron ? launch_kron(batch, nb, H, nullptr, nullptr, s) : stack ? launch_stack(batch, nb, H, nullptr, nullptr, s) : launch_large(batch, nb, H, nullptr, nullptr, s))) return rc;
                 nb = 0;
             }
         }
-        if (nb > 0 && (rc = kron ? launch_kron(batch, nb, H, nullptr, nullptr, s) : launch_stack(batch, nb, H, nullptr, nullptr, s))) return rc;
+        if (nb > 0 && (rc = kron ? launch_kron(batch, nb, H, nullptr, nullptr, s) : stack ? launch_stack(batch, nb, H, nullptr, nullptr, s) : launch_large(batch, nb, H, nullptr, nullptr, s))) return rc;
     }
     for (int i : single) {
         const int rc = dctp_score_accum(sites[i].x, sites[i].B, H, W, static_cast<long long>(sites[i].c_count) * H * W, static_cast<long long>(H) * W, W, 0,

@@ -38,22 +38,31 @@
 
 namespace dctp {
 
-struct LargeTensorMap { CUtensorMap m; };   // the activation as [n_maps * N rows, N floats], box {64, 128}
+constexpr int LARGE_MAX_SEG = 16;           // activations (hook sites of the same map side) one launch can score
+// one tensor map per activation of the launch: [n_maps * N rows, N floats], box {64, 128}
+struct LargeTensorMap { CUtensorMap m[LARGE_MAX_SEG]; };
+// The activations of a launch, all their scored maps back to back.  Work item i belongs to segment s with item0[s] <= i < item0[s + 1]
+// (every segment holds a whole number of NVC-item maps, so i % NVC is still the v-chunk).
+struct LargeSegments {
+    int n_seg;
+    int item0[LARGE_MAX_SEG + 1];
+    int c_count[LARGE_MAX_SEG];
+    double* accum[LARGE_MAX_SEG];
+};
 
 struct LargeScoreArgs {
-    const float* x_dense;           // first scored element; all scored maps back to back (stride_h == N), 16-B aligned
-    int n_maps, c_count;
+    LargeSegments seg;
+    int n_maps;                     // all segments together
     int N, NPR;                     // map side; rows per column block of the basis image (>= N and >= NU * NUC, zero padded)
     int NVC;                        // v-chunks per map = ceil(N / 128)
     int NU, NUC;                    // u-chunk width (multiple of 16, <= 128) and count: NU * NUC >= N
     int n_items;                    // n_maps * NVC
     const uint8_t* c_hi;            // basis image, bf16: [column blocks of 64][NPR rows][128 B], 16-B chunks XOR-swizzled by
     const uint8_t* c_lo;            //   (row & 7): any (8-aligned row range, column block) is one contiguous operand slab
-    double* accum;
     float* energy_out;              // (unused by the kernel: the host sums energy_parts into it)
-    float* energy_parts;            // optional [n_maps][NVC]: each work item's share of its map's energy; summed in a fixed order by
+    float* energy_parts;            // optional (single-segment launches only) [n_maps][NVC]: each work item's share of its map's energy; summed in a fixed order by
                                     // sum_parts_kernel, so per-map energies are bit-reproducible like the other kernels'
-    float* dump;                    // optional [n_maps][N][N] coefficients Z[u][v]
+    float* dump;                    // optional (single-segment launches only) [n_maps][N][N] coefficients Z[u][v]
     int* status;
     long long* trace;               // bring-up aid: cycles the control thread of CTA 0 spent in each kind of wait
 };
@@ -272,16 +281,18 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const __grid_c
         // =========================================================== map producer: one elected thread, one TMA per map slab,
         //     in the order the converters consume them: (item, h-tile, 64-wide w block)
         if (elect_one()) {
-            tma_prefetch_desc(&xmap.m);
+            tma_prefetch_desc(&xmap.m[0]);
             uint32_t k = 0;
+            int sg = 0;
             for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-                const int row0 = (item / a.NVC) * N;
+                while (item >= a.seg.item0[sg + 1]) ++sg;
+                const int row0 = ((item - a.seg.item0[sg]) / a.NVC) * N;
                 for (int h0 = 0; h0 < N; h0 += 128)
                     for (int w0 = 0; w0 < N; w0 += 64, ++k) {
                         const uint32_t set = k & 1u;
                         if (k >= 2) wait(stg_free + set, ((k >> 1) - 1u) & 1u);
                         mbar_arrive_expect_tx(stg_full + set, S::STAGE_BUF);
-                        tma_load_2d(smem + S::OFF_STAGE + set * S::STAGE_BUF, &xmap.m, w0, row0 + h0, stg_full + set);
+                        tma_load_2d(smem + S::OFF_STAGE + set * S::STAGE_BUF, &xmap.m[sg], w0, row0 + h0, stg_full + set);
                     }
             }
         }
@@ -337,8 +348,10 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const __grid_c
         const int NB = (N + 63) >> 6;                              // 64-wide w blocks per tile
         const int PS = min((int)S::NXB, NB);                       // slabs of the following tile stored ahead of time
         int first_block = 0;                                       // this tile's slabs [0, first_block) are already stored
+        int sg = 0;
         for (; item < a.n_items; item += gridDim.x) {
-            const int map = item / a.NVC, vc = item - map * a.NVC;
+            while (item >= a.seg.item0[sg + 1]) ++sg;
+            const int map = (item - a.seg.item0[sg]) / a.NVC, vc = item % a.NVC;       // map within its segment, v-chunk
             const int v0 = vc * 128, MV = min(128, N - v0);
             const int nitem = item + (int)gridDim.x;               // what this CTA works on next
 
@@ -420,7 +433,7 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const __grid_c
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (tid == 0) {
-                    atomicAdd(a.accum + (map % a.c_count), (double)s);
+                    atomicAdd(a.seg.accum[sg] + (map % a.seg.c_count[sg]), (double)s);
                     if (a.energy_parts) a.energy_parts[(size_t)map * a.NVC + vc] = s;
                 }
             }

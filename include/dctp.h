@@ -85,7 +85,7 @@ int dctp_score_accum(const float* x, int B, int H, int W,
  * (dct_pruning_b200.hooks.ScoreSession does: the deferred form of get_feature_hook, utils/common.py:262-277, one call per run of
  * same-sized sites instead of one per site).  Every site is DENSE: x points at its first scored map (the channel window already
  * applied) and B * c_count maps of H x W floats follow back to back; accum as in dctp_score_accum.  Map sizes the multi-site
- * kernels take (square, side <= 8, or even side 10..64 - above 32 a multiple of 4) are scored SCORE_MAX_SEG = 16 sites per launch;
+ * kernels take (square; side <= 8, even side 10..64 - above 32 a multiple of 4 -, or side 80..320 a multiple of 16) are scored 16 sites per launch;
  * any other shape falls back to one launch per site.  Results are identical to n_sites dctp_score_accum calls. */
 typedef struct dctp_site {
     const float* x;

@@ -160,7 +160,7 @@ def test_cuda_graph_replay_matches_eager(lib, cuda_device):
 
 
 @pytest.mark.parametrize('net_name,batch,side', [('resnet_56', 16, 32), ('vgg_16_bn', 8, 32), ('googlenet', 4, 32), ('densenet_40', 4, 32),
-                                                 ('resnet_50', 2, 224), ('u2netp', 2, 160)])
+                                                 ('resnet_50', 2, 224), ('u2netp', 2, 160), ('u2netp', 1, 320)])
 def test_multi_site_launches_match_one_launch_per_site(lib, cuda_device, net_name, batch, side):
     """Small activations are held and scored up to 16 sites per launch (dctp_score_accum_multi).  Same numbers as one launch per
     site (fp64 sums in another order: 1e-12), far fewer launches, and no held activation was overwritten before it was read."""
