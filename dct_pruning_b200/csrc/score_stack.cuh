@@ -82,7 +82,8 @@ struct StackSmem {
     static constexpr uint32_t LBO2 = 64 * 16 + 16;                       // stage-2 basis, same layout
     static constexpr uint32_t C2_HALF = 8 * LBO2;                        // 8320
     static constexpr uint32_t OFF_BX = NSTG * STG_STRIDE;
-    static constexpr uint32_t OFF_C2 = OFF_BX + 4 * BX_HALF;
+    static constexpr uint32_t NBX = 3;                                   // room for three Bx buffers (hi | lo each); how many a kernel uses: see NBXK
+    static constexpr uint32_t OFF_C2 = OFF_BX + 2 * NBX * BX_HALF;
     static constexpr uint32_t OFF_TABLE = OFF_C2 + 2 * C2_HALF;
     static constexpr uint32_t TABLE_MAX = 8192;
     static constexpr uint32_t OFF_RED = OFF_TABLE + TABLE_MAX;
@@ -110,6 +111,9 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
     constexpr int G = KP == 16 ? 8 : KP == 32 ? 4 : 2, T2 = G / 2;
     constexpr uint32_t W_E1 = NCONV, W_E2 = NCONV + 8 * NE1G, W_PROD = W_E2 + 4 * NE2G, W_MMA = W_PROD + 1, W_MMA2 = W_PROD + 2, NT = (W_MMA2 + 1) * 32;
     constexpr uint32_t NCT = NCONV * 32 / NCG;                            // threads that convert one tile
+    // Bx buffers in use: with three the converters run a tile further ahead of stage 1 (same box: 56x56 4.25 -> 4.59 TB/s, 64-channel launches
+    // 3.74 -> 4.1, 14x14 3.55 -> 3.6; at KP = 32 it loses, 28x28 3.95 -> 3.60, so those instantiations keep two)
+    constexpr uint32_t NBXK = KP == 32 ? 2u : 3u;
     constexpr uint32_t TM_A = 0, TM_D1 = 32;                              // TMEM columns: A | D1 x 2 | A2 x 2 (64 each) | D2 x NB2 (64 each)
     const uint32_t d1_stride = a.ncols <= 112 ? 112u : 128u;
     const uint32_t TM_A2 = TM_D1 + 2 * d1_stride, TM_D2 = TM_A2 + 128;
@@ -128,14 +132,14 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);
     uint64_t* stg_full = bars;                                            // [3] TMA landed (tx bytes)
     uint64_t* stg_free = bars + 3;                                        // [3] NCONV converter warps
-    uint64_t* bx_full = bars + 6;                                         // [2] NCONV converter warps
-    uint64_t* bx_free = bars + 8;                                         // [2] stage-1 MMAs of the buffer have completed
-    uint64_t* d1_full = bars + 10;                                        // [2] ... and D1 is complete
-    uint64_t* d1_free = bars + 12;                                        // [2] 8 epilogue-1 warps have read it
-    uint64_t* a2_full = bars + 14;                                        // [2] 8 epilogue-1 warps have written A2
-    uint64_t* a2_free = bars + 16;                                        // [2] stage-2 MMAs have read it
-    uint64_t* d2_full = bars + 18;                                        // [2]
-    uint64_t* d2_free = bars + 20;                                        // [2] 4 epilogue-2 warps
+    uint64_t* bx_full = bars + 6;                                         // [3] the converter warps of the tile's group
+    uint64_t* bx_free = bars + 9;                                         // [3] stage-1 MMAs of the buffer have completed
+    uint64_t* d1_full = bars + 12;                                        // [2] ... and D1 is complete
+    uint64_t* d1_free = bars + 14;                                        // [2] 8 epilogue-1 warps have read it
+    uint64_t* a2_full = bars + 16;                                        // [2] 8 epilogue-1 warps have written A2
+    uint64_t* a2_free = bars + 18;                                        // [2] stage-2 MMAs have read it
+    uint64_t* d2_full = bars + 20;                                        // [2]
+    uint64_t* d2_free = bars + 22;                                        // [2] 4 epilogue-2 warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::OFF_SLOT);
 
     long long tr_entry = 0;                                               // (debug instantiation) wall-clock stamps of the launch's phases
@@ -145,8 +149,8 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
     if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         for (int s = 0; s < 3; ++s) { mbar_init(stg_full + s, 1); mbar_init(stg_free + s, NCONV / NCG); }
+        for (int b = 0; b < (int)S::NBX; ++b) { mbar_init(bx_full + b, NCONV / NCG); mbar_init(bx_free + b, 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bx_full + b, NCONV / NCG); mbar_init(bx_free + b, 1);
             mbar_init(d1_full + b, 1); mbar_init(d1_free + b, 8);
             mbar_init(a2_full + b, 8); mbar_init(a2_free + b, 1);
             mbar_init(d2_full + b, 1); mbar_init(d2_free + b, 4);              // (4 warps of ONE epilogue-2 group read a tile)
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
 #pragma unroll
             for (int i = 0; i < 8; ++i) ai[i] = reinterpret_cast<const uint4*>(a.a_img + tid * 32)[i];
         }
-        for (uint32_t off = ptid * 16; off < 4 * S::BX_HALF; off += PNT * 16) *reinterpret_cast<uint4*>(bx + off) = make_uint4(0, 0, 0, 0);
+        for (uint32_t off = ptid * 16; off < 2 * S::NBX * S::BX_HALF; off += PNT * 16) *reinterpret_cast<uint4*>(bx + off) = make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const uint32_t off = (ptid + i * PNT) * 16;
@@ -270,15 +274,15 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
             const uint64_t desc = make_smem_desc(0, a.lbo1, 128, SWIZZLE_NONE);
             uint32_t n = 0;
             for (int tile = first; tile < a.num_tiles; tile += stride, ++n) {
-                const uint32_t b = n & 1u;
+                const uint32_t b = n & 1u, bb = n % NBXK;                  // D1 buffer, Bx buffer
                 TR_START();
-                if (!mbar_wait(bx_full + b, (n >> 1) & 1u)) { dead = true; break; }
+                if (!mbar_wait(bx_full + bb, (n / NBXK) & 1u)) { dead = true; break; }
                 TR_ADD(tr0);
                 if (n >= 2 && !mbar_wait(d1_free + b, ((n >> 1) - 1u) & 1u)) { dead = true; break; }
                 TR_ADD(tr1);
                 tc_fence_after_sync();
                 const uint32_t d1 = tmem + TM_D1 + b * d1_stride;
-                const uint32_t lo_hi = static_cast<uint32_t>(desc) + (smem_u32(bx + b * 2 * S::BX_HALF) >> 4);
+                const uint32_t lo_hi = static_cast<uint32_t>(desc) + (smem_u32(bx + bb * 2 * S::BX_HALF) >> 4);
                 const uint32_t lo_lo = lo_hi + (S::BX_HALF >> 4);
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass)
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
                         mma_bf16_ts(d1, tmem + TM_A + 8 * ks, desc_with_lo(desc, (pass ? lo_lo : lo_hi) + ks * STEP1), a.idesc1,
                                     (pass | ks) != 0);
                 mma_commit(d1_full + b);
-                mma_commit(bx_free + b);
+                mma_commit(bx_free + bb);
                 TR_ADD(tr2);
             }
             TR_FLUSH(8);
@@ -345,11 +349,11 @@ __global__ void __launch_bounds__((NCONV + 8 * NE1G + 4 * NE2G + 3) * 32, 1) sco
                 if (!tail) ++it;
                 continue;
             }
-            const uint32_t b = n & 1u, s = it % S::NSTG;
+            const uint32_t b = n % NBXK, s = it % S::NSTG;
             TR_START();
             {
                 bool ok = true;
-                if (n >= 2) ok = mbar_wait(bx_free + b, ((n >> 1) - 1u) & 1u);
+                if (n >= NBXK) ok = mbar_wait(bx_free + b, ((n / NBXK) - 1u) & 1u);
                 TR_ADD(tr0);
                 if (ok && !tail) ok = mbar_wait(stg_full + s, (it / S::NSTG) & 1u);
                 TR_ADD(tr1);
