@@ -442,6 +442,9 @@ __global__ void __launch_bounds__(LARGE_NT, 1) score_large_kernel(const __grid_c
         if (TRACE && a.trace != nullptr && blockIdx.x == 0 && tid == 0)
             for (int i = 0; i < 5; ++i) a.trace[8 + i] = ctr[i];
     }
+    if (dead && (tid & 31u) == 0)                                  // a hand-over never came (status word set): poison the result
+        for (int sgi = 0; sgi < a.seg.n_seg; ++sgi)
+            for (int c = 0; c < a.seg.c_count[sgi]; ++c) a.seg.accum[sgi][c] = __longlong_as_double(0x7FF8000000000000ll);
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem);

@@ -632,7 +632,10 @@ __global__ void __launch_bounds__(128, KP == 64 ? 4 : 1) score_umma_kernel(const
         tile = next;
     }
 
-    if (!alive && tid == 0) atomicExch(a.status, DCTP_DEV_MMA_TIMEOUT);
+    if (!alive && tid == 0) {                                      // a hand-over never came: flag it and poison the result
+        atomicExch(a.status, DCTP_DEV_MMA_TIMEOUT);
+        for (int c = 0; c < a.c_count; ++c) a.accum[c] = __longlong_as_double(0x7FF8000000000000ll);
+    }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<S::TMEM_COLS>(tmem);
