@@ -327,6 +327,55 @@ def measure_net(args, net_name, side, B, rank, local_rank, world, device, lib, s
     by_kernel = table(lambda i: site_kernel[i])
     by_shape = table(lambda i: '%dx%dx%d' % (scored[i], acts[i].shape[2], acts[i].shape[3]))
     out.update(by_kernel=by_kernel, by_shape=by_shape)
+    # ---- the launches of the timed step as they really are (multi-site launches: all sites of a map side in one or two launches),
+    #      an event pair around each, per map side.  by_shape above times one launch per site, where the ~10 us a launch costs beyond
+    #      its bytes weighs on the small layers; this table shows what those layers cost inside the step.  Informational: a failure
+    #      here must not take the bench line with it.
+    try:
+        session.reset()
+        pairs = []
+        raw_single, raw_multi = session._score_accum, session._score_multi
+
+        def timed_launch(fn, side_arg):
+            def call(*a):
+                e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e_a.record()
+                rc = fn(*a)
+                e_b.record()
+                pairs.append((int(a[side_arg]), e_a, e_b))
+                return rc
+            return call
+        session._score_accum, session._score_multi = timed_launch(raw_single, 2), timed_launch(raw_multi, 2)
+        try:
+            for _ in range(steps):
+                one_step()
+            torch.cuda.synchronize()
+        finally:
+            session._score_accum, session._score_multi = raw_single, raw_multi
+        side_tot = {}
+        for i in live:
+            d = side_tot.setdefault(int(acts[i].shape[2]), {'bytes': 0, 'roofline_s': 0.0, 'sites': 0})
+            d['bytes'] += roof[i][0]
+            d['roofline_s'] += roof[i][2]
+            d['sites'] += 1
+        side_ms, side_n = {}, {}
+        for side_h, e_a, e_b in pairs:
+            side_ms[side_h] = side_ms.get(side_h, 0.0) + e_a.elapsed_time(e_b)
+            side_n[side_h] = side_n.get(side_h, 0) + 1
+        by_side = {}
+        for side_h, d in sorted(side_tot.items(), reverse=True):
+            if side_h not in side_ms:
+                continue
+            sec = side_ms[side_h] / steps / 1e3
+            by_side['%dx%d' % (side_h, side_h)] = {'sites': d['sites'], 'launches_per_step': round(side_n[side_h] / steps, 2),
+                                                   'ms_per_step': round(sec * 1e3, 4), 'bytes_per_step': d['bytes'],
+                                                   'GBps': round(d['bytes'] / sec / 1e9, 1), 'frac_hbm': round(d['bytes'] / sec / 1e9 / hbm_peak, 3),
+                                                   'frac': round(d['roofline_s'] / sec, 3)}
+        out['by_side_in_step'] = by_side
+        session.reset()
+    except Exception as exc:                                         # noqa: BLE001
+        out['by_side_in_step'] = {'error': repr(exc)}
+        session.reset()
     if by_kernel:
         dom_name = max(by_kernel, key=lambda k: by_kernel[k]['ms_per_step'])       # dominant = largest share of the step
         dom = by_kernel[dom_name]
@@ -533,11 +582,12 @@ def run_ours(args):
                        'parallelism': 'batch-sharded x%d, 1 all-reduce per run' % world,
                        'peaks': {'hbm_gbs': hbm_peak, 'bf16_tflops_sustained': tflops, 'kind': peak_kind}},
             'gpu_launches': main['gpu_launches'],
-            'launch_batching': 'activations below 1 GB are held and scored up to 16 sites of a map size per launch (dctp_score_accum_multi); by_kernel / by_shape time one launch per site',
+            'launch_batching': 'activations below 1 GB are held and scored up to 16 sites of a map size per launch (dctp_score_accum_multi); by_kernel / by_shape time one launch per site, by_side_in_step the launches of the timed step themselves (an event pair around each)',
             'roofline': main.get('roofline'),
             'hook_path_GBps': main['hook_path_GBps'],
             'binding_roofline_frac': main['binding_roofline_frac'],
             'by_kernel': main['by_kernel'], 'by_shape': main['by_shape'],
+            'by_side_in_step': main.get('by_side_in_step'),
             'clocks': clocks,
         }
         if 'e2e' in main:
